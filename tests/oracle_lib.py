@@ -1,0 +1,183 @@
+"""ctypes loader for oracle/liboracle.so — TEST INFRASTRUCTURE ONLY (the CPU checker)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+U64P = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(ROOT, "oracle", "liboracle.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+        _LIB = C.CDLL(path)
+        _LIB.orc_last_error.restype = C.c_char_p
+    return _LIB
+
+
+def _chk(rc):
+    if rc != 0:
+        raise RuntimeError("oracle: " + lib().orc_last_error().decode())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def field_op(field, op, a, b=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.empty_like(a)
+    if b is not None:
+        b = np.ascontiguousarray(b, dtype=np.uint64)
+    _chk(lib().orc_field_op(field, op, _p(a), _p(b), _p(out), C.c_size_t(a.size // 4)))
+    return out
+
+
+def to_mont(field, canon):
+    canon = np.ascontiguousarray(canon, dtype=np.uint64)
+    out = np.empty_like(canon)
+    _chk(lib().orc_to_mont(field, _p(canon), _p(out), C.c_size_t(canon.size // 4)))
+    return out
+
+
+def from_mont(field, mont):
+    mont = np.ascontiguousarray(mont, dtype=np.uint64)
+    out = np.empty_like(mont)
+    _chk(lib().orc_from_mont(field, _p(mont), _p(out), C.c_size_t(mont.size // 4)))
+    return out
+
+
+def fr_from_u512(wide):
+    wide = np.ascontiguousarray(wide, dtype=np.uint64)
+    n = wide.size // 8
+    out = np.empty((n, 4), dtype=np.uint64)
+    _chk(lib().orc_fr_from_u512(_p(wide), _p(out), C.c_size_t(n)))
+    return out
+
+
+def fr_const(which):
+    out = np.empty(4, dtype=np.uint64)
+    _chk(lib().orc_fr_const(which, _p(out)))
+    return out
+
+
+def g1_op(op, a, b=None):
+    out = np.empty(8, dtype=np.uint64)
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if b is not None:
+        b = np.ascontiguousarray(b, dtype=np.uint64)
+    _chk(lib().orc_g1_op(op, _p(a), _p(b), _p(out)))
+    return out
+
+
+def g1_on_curve(pts):
+    pts = np.ascontiguousarray(pts, dtype=np.uint64)
+    return bool(lib().orc_g1_on_curve(_p(pts), C.c_size_t(pts.size // 8)))
+
+
+def msm(scalars, bases, threads=1):
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+    bases = np.ascontiguousarray(bases, dtype=np.uint64)
+    n = scalars.size // 4
+    assert bases.size // 8 == n
+    out = np.empty(8, dtype=np.uint64)
+    _chk(lib().orc_msm(_p(scalars), _p(bases), C.c_size_t(n), threads, _p(out)))
+    return out
+
+
+def fft(a, omega, log_n, threads=1):
+    a = np.array(a, dtype=np.uint64, copy=True)
+    omega = np.ascontiguousarray(omega, dtype=np.uint64)
+    assert a.size == 4 << log_n
+    _chk(lib().orc_fft(_p(a), _p(omega), log_n, threads))
+    return a
+
+
+def domain(j, k):
+    ek = C.c_uint(0)
+    om = np.empty((4, 4), dtype=np.uint64)
+    _chk(lib().orc_domain(j, k, C.byref(ek), _p(om)))
+    return ek.value, om
+
+
+def domain_op(j, k, which, a, threads=1):
+    ek, _ = domain(j, k)
+    n = 1 << k
+    out_len = {0: n, 1: n, 2: 1 << ek, 3: n * (j - 1), 4: 1 << ek}[which]
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.empty((out_len, 4), dtype=np.uint64)
+    _chk(lib().orc_domain_op(j, k, which, _p(a), _p(out), threads))
+    return out
+
+
+def g_to_lagrange(g, k, threads=1):
+    g = np.ascontiguousarray(g, dtype=np.uint64)
+    out = np.empty((1 << k, 8), dtype=np.uint64)
+    _chk(lib().orc_g_to_lagrange(_p(g), k, _p(out), threads))
+    return out
+
+
+def eval_polynomial(poly, x):
+    poly = np.ascontiguousarray(poly, dtype=np.uint64)
+    x = np.ascontiguousarray(x, dtype=np.uint64)
+    out = np.empty(4, dtype=np.uint64)
+    _chk(lib().orc_eval_polynomial(_p(poly), C.c_size_t(poly.size // 4), _p(x), _p(out)))
+    return out
+
+
+def keccak256(data: bytes) -> bytes:
+    out = C.create_string_buffer(32)
+    lib().orc_keccak256(data, C.c_size_t(len(data)), out)
+    return out.raw
+
+
+def smallrng(seed, n):
+    out = np.empty(n, dtype=np.uint64)
+    lib().orc_smallrng(C.c_uint64(seed), _p(out), C.c_size_t(n))
+    return out
+
+
+def chacha20(seed32: bytes, n):
+    out = np.empty(n, dtype=np.uint64)
+    lib().orc_chacha20(seed32, _p(out), C.c_size_t(n))
+    return out
+
+
+def random_fr(seed, n):
+    out = np.empty((n, 4), dtype=np.uint64)
+    lib().orc_random_fr(C.c_uint64(seed), _p(out), C.c_size_t(n))
+    return out
+
+
+def srs_read(path, fmt):
+    """fmt 0 = halo2 RawBytes, 1 = .ptau.  Returns dict(k, g, g_lagrange|None, g2, s_g2)."""
+    k = C.c_uint(0)
+    _chk(lib().orc_srs_read(path.encode(), fmt, C.byref(k), None, None, None))
+    n = 1 << k.value
+    g = np.empty((n, 8), dtype=np.uint64)
+    gl = np.empty((n, 8), dtype=np.uint64) if fmt == 0 else None
+    g2s = np.empty((2, 16), dtype=np.uint64)
+    _chk(lib().orc_srs_read(path.encode(), fmt, C.byref(k), _p(g), _p(gl), _p(g2s)))
+    return dict(k=k.value, g=g, g_lagrange=gl, g2=g2s[0].copy(), s_g2=g2s[1].copy())
+
+
+def pairing_check(p1, q1, p2, q2):
+    ok = C.c_int(0)
+    arrs = [np.ascontiguousarray(x, dtype=np.uint64) for x in (p1, q1, p2, q2)]
+    _chk(lib().orc_pairing_check(*[_p(x) for x in arrs], C.byref(ok)))
+    return bool(ok.value)
+
+
+def g2_on_curve(q):
+    q = np.ascontiguousarray(q, dtype=np.uint64)
+    return bool(lib().orc_g2_on_curve(_p(q)))
+
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+RAW11 = os.path.join(GOLDEN, "ppot_0080_11_raw.bin")
