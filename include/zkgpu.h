@@ -1,0 +1,93 @@
+/* libzkgpu — C ABI of the B200-native BN254 proving backend.
+ *
+ * This is the drop-in boundary for the data-parallel core of Shielder's halo2 prover.  halo2 v0.3.0
+ * has no backend trait: `best_multiexp` / `best_fft` are free functions in un-vendored dependencies
+ * (halo2curves 0.6.1 msm.rs / fft.rs, halo2_proofs v0.3.0 arithmetic.rs, poly/domain.rs,
+ * poly/kzg/commitment.rs — /root/reference/Cargo.lock:2332-2334,2367-2368), reached from the
+ * reference only through
+ *     shielder_circuits::generate_proof(&params, &pk, circuit, &public_input, rng)
+ *       (/root/reference/crates/shielder_bindings/src/circuits/mod.rs:103-111,
+ *        /root/reference/crates/shielder-account/src/call_data.rs:489-501,
+ *        /root/reference/tee/crates/shielder-prover-tee/src/circuits/mod.rs:70-78)
+ * and the ParamsKZG data seam (/root/reference/crates/powers-of-tau/lib.rs:64,71,263,280).
+ * Each entry point below names the upstream function whose body a `[patch]`ed halo2curves /
+ * halo2_proofs would replace with a call to it (binding shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - Field elements: 4 x u64, little-endian limbs, Montgomery form (R = 2^256) — the in-memory
+ *     layout of Rust `bn256::Fr` / `Fq` and of halo2 `SerdeFormat::RawBytes`
+ *     (verified on /root/reference/resources/ppot_0080_11_raw).
+ *   - G1 affine: (x, y) as 8 x u64; identity = (0,0) (`G1Affine::identity()`).
+ *   - G1 projective results: Jacobian (X, Y, Z) as 12 x u64, returned normalised (Z = 1, or
+ *     (0,1,0) for the identity) — projective representatives are not canonical, the group element is.
+ *   - All pointers are host memory unless the function name ends in `_dev`.
+ *   - All functions are synchronous, thread-safe, return 0 on success and a negative code otherwise;
+ *     zkgpu_last_error() gives the thread-local message.  The upstream functions are infallible and
+ *     panic on misuse; the Rust shim maps a non-zero return to `panic!`.
+ *   - There is no CPU fallback: without a CUDA device every compute call fails with ZKGPU_ERR_CUDA.
+ */
+#ifndef ZKGPU_H
+#define ZKGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKGPU_OK 0
+#define ZKGPU_ERR_CUDA (-1)
+#define ZKGPU_ERR_ARG (-2)
+#define ZKGPU_ERR_STATE (-3)
+#define ZKGPU_ERR_INTERNAL (-4)
+
+/* Binds the calling process to the CUDA device `device` (one process per GPU). Idempotent. */
+int zkgpu_init(int device);
+void zkgpu_shutdown(void);
+const char* zkgpu_last_error(void);
+/* ABI version of this header (bumped on any signature change). */
+int zkgpu_abi_version(void);
+
+/* ---- MSM: halo2curves::msm::best_multiexp(coeffs, bases) -> G1 -------------------------------- */
+int zkgpu_msm_g1(const uint64_t* scalars, const uint64_t* bases_affine, size_t n, uint64_t out_jacobian[12]);
+
+/* ---- SRS-resident MSM: ParamsKZG::{commit, commit_lagrange} (poly/kzg/commitment.rs) -----------
+ * zkgpu_srs_register uploads g and g_lagrange (n = 2^k points each, as ParamsKZG holds them;
+ * crates/powers-of-tau/lib.rs:71 builds it, :280 `get_g`) once and precomputes the fixed-base window
+ * tables.  basis: 0 = g (monomial, `commit`), 1 = g_lagrange (`commit_lagrange`). */
+int zkgpu_srs_register(const uint64_t* g, const uint64_t* g_lagrange, uint32_t k, uint64_t* handle_out);
+int zkgpu_srs_release(uint64_t srs);
+int zkgpu_msm_g1_srs(uint64_t srs, int basis, const uint64_t* scalars, size_t n, uint64_t out_jacobian[12]);
+/* m independent commitments over the same basis in one launch; scalars is m x n, out is m x 8 (affine). */
+int zkgpu_msm_g1_srs_batch(uint64_t srs, int basis, const uint64_t* scalars, size_t n, size_t m, uint64_t* out_affine);
+
+/* ---- NTT: halo2curves::fft::best_fft::<Fr, Fr>(a, omega, log_n), in place, natural order ------- */
+int zkgpu_ntt_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_n);
+int zkgpu_ntt_fr_batch(uint64_t* a /* m x n */, const uint64_t omega[4], uint32_t log_n, size_t m);
+
+/* ---- EvaluationDomain (halo2_proofs poly/domain.rs) ------------------------------------------- */
+/* lagrange_to_coeff (inverse=1) / coeff_to_lagrange (inverse=0) on m polynomials of 2^k values */
+int zkgpu_domain_ntt_fr(uint64_t* a, uint32_t k, int inverse, size_t m);
+/* coeff_to_extended: n = 2^k coefficients -> 2^ext_k evaluations on the zeta-coset */
+int zkgpu_coset_ntt_fr(const uint64_t* coeffs, uint32_t k, uint32_t ext_k, uint64_t* out);
+/* extended_to_coeff: 2^ext_k coset evaluations (in place) -> coefficients; the first
+ * 2^k * quotient_degree entries are the result (the upstream `truncate`), the rest is zeroed. */
+int zkgpu_coset_intt_fr(uint64_t* evals, uint32_t k, uint32_t ext_k, uint32_t quotient_degree);
+
+/* ---- G1 FFT: best_fft::<Fr, G1> as used by g_to_lagrange (ParamsKZG::from_parts / downsize) ----
+ * points: n x 12 u64 Jacobian, transformed in place and returned normalised (Z = 1). */
+int zkgpu_fft_g1(uint64_t* points_jacobian, const uint64_t omega[4], uint32_t log_n);
+/* g_to_lagrange(g, k): n^-1 * FFT_{omega^-1}(g), affine in, affine out */
+int zkgpu_g_to_lagrange(const uint64_t* g_affine, uint32_t k, uint64_t* out_affine);
+
+/* ---- device-resident variants (inputs already in HBM; `stream` is a cudaStream_t or NULL) ------
+ * Used by the prover pipeline and by bench.py's kernel-only ("value") measurement. */
+int zkgpu_ntt_fr_batch_dev(void* d_a, const uint64_t omega[4], uint32_t log_n, size_t m, void* d_scratch, void* stream);
+int zkgpu_msm_g1_srs_batch_dev(uint64_t srs, int basis, const void* d_scalars, size_t n, size_t m, void* d_out_affine, void* stream);
+/* number of kernel launches issued by this library in this process so far */
+uint64_t zkgpu_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKGPU_H */

@@ -1,0 +1,59 @@
+// Shared host-side plumbing for libzkgpu: error type, CUDA checks, RAII device buffers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <atomic>
+
+namespace zk {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+enum { ZK_OK = 0, ZK_ERR_CUDA = -1, ZK_ERR_ARG = -2, ZK_ERR_STATE = -3, ZK_ERR_INTERNAL = -4 };
+
+#define ZK_CUDA(x)                                                                                   \
+    do {                                                                                             \
+        cudaError_t e_ = (x);                                                                        \
+        if (e_ != cudaSuccess)                                                                       \
+            throw zk::Error(zk::ZK_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_) + " @" + \
+                                                 __FILE__ + ":" + std::to_string(__LINE__));         \
+    } while (0)
+#define ZK_REQUIRE(c, msg) \
+    do { if (!(c)) throw zk::Error(zk::ZK_ERR_ARG, std::string(msg)); } while (0)
+
+extern std::atomic<uint64_t> g_launches;  // kernels launched by this library (zkgpu_launch_count)
+#define ZK_LAUNCH(kern, grid, block, smem, st, ...)        \
+    do {                                                   \
+        kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__); \
+        ++zk::g_launches;                                  \
+        ZK_CUDA(cudaGetLastError());                       \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        if (count) ZK_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        n = count;
+    }
+    void ensure(size_t count) { if (count > n) alloc(count); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+static inline unsigned ceil_div(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace zk

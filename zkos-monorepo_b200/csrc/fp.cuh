@@ -1,0 +1,120 @@
+// BN254 field elements on the device: 8 x u32 limbs, little-endian, Montgomery form (R = 2^256).
+// Byte-identical to the host/Rust layout (4 x u64 LE Montgomery — halo2curves bn256::Fr/Fq memory,
+// SURVEY.md §8a row a1), so buffers cross the C ABI without any repacking.
+// The limb arithmetic itself is generated (gen_fp.py -> fp_gen.inc): PTX mad.lo.cc/madc.hi.cc carry
+// chains that ptxas fuses into IMAD.WIDE.U32.X — 128 wide multiply-adds per Montgomery product.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "fp_gen.inc"
+
+namespace zk {
+
+struct FrTag {};
+struct FqTag {};
+
+template <class Tag>
+struct __align__(16) Fe {
+    uint32_t l[8];
+
+    __host__ __device__ __forceinline__ static Fe zero() {
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.l[i] = 0;
+        return r;
+    }
+    __host__ __device__ __forceinline__ bool is_zero() const {
+        return (l[0] | l[1] | l[2] | l[3] | l[4] | l[5] | l[6] | l[7]) == 0;
+    }
+    __host__ __device__ __forceinline__ bool operator==(const Fe& o) const {
+        uint32_t d = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d |= l[i] ^ o.l[i];
+        return d == 0;
+    }
+    __host__ __device__ __forceinline__ bool operator!=(const Fe& o) const { return !(*this == o); }
+};
+typedef Fe<FrTag> fr_t;
+typedef Fe<FqTag> fq_t;
+
+// ---- per-field dispatch ---------------------------------------------------------------------
+__host__ __device__ __forceinline__ fr_t operator*(const fr_t& a, const fr_t& b) { fr_t r; fr_mul(r.l, a.l, b.l); return r; }
+__host__ __device__ __forceinline__ fr_t operator+(const fr_t& a, const fr_t& b) { fr_t r; fr_add(r.l, a.l, b.l); return r; }
+__host__ __device__ __forceinline__ fr_t operator-(const fr_t& a, const fr_t& b) { fr_t r; fr_sub(r.l, a.l, b.l); return r; }
+__host__ __device__ __forceinline__ fr_t sqr(const fr_t& a) { fr_t r; fr_sqr(r.l, a.l); return r; }
+__host__ __device__ __forceinline__ fq_t operator*(const fq_t& a, const fq_t& b) { fq_t r; fq_mul(r.l, a.l, b.l); return r; }
+__host__ __device__ __forceinline__ fq_t operator+(const fq_t& a, const fq_t& b) { fq_t r; fq_add(r.l, a.l, b.l); return r; }
+__host__ __device__ __forceinline__ fq_t operator-(const fq_t& a, const fq_t& b) { fq_t r; fq_sub(r.l, a.l, b.l); return r; }
+__host__ __device__ __forceinline__ fq_t sqr(const fq_t& a) { fq_t r; fq_sqr(r.l, a.l); return r; }
+
+__host__ __device__ __forceinline__ void fe_set_one(fr_t& r) { fr_set_one(r.l); }
+__host__ __device__ __forceinline__ void fe_set_one(fq_t& r) { fq_set_one(r.l); }
+__host__ __device__ __forceinline__ void fe_set_r2(fr_t& r) { fr_set_r2(r.l); }
+__host__ __device__ __forceinline__ void fe_set_r2(fq_t& r) { fq_set_r2(r.l); }
+__host__ __device__ __forceinline__ void fe_set_modm2(fr_t& r) { fr_set_modm2(r.l); }
+__host__ __device__ __forceinline__ void fe_set_modm2(fq_t& r) { fq_set_modm2(r.l); }
+
+template <class Tag>
+__host__ __device__ __forceinline__ Fe<Tag> fe_one() { Fe<Tag> r; fe_set_one(r); return r; }
+template <class Tag>
+__host__ __device__ __forceinline__ Fe<Tag> fe_r2() { Fe<Tag> r; fe_set_r2(r); return r; }
+template <class Tag>
+__host__ __device__ __forceinline__ Fe<Tag> neg(const Fe<Tag>& a) {
+    return a.is_zero() ? a : Fe<Tag>::zero() - a;
+}
+template <class Tag>
+__host__ __device__ __forceinline__ Fe<Tag> dbl(const Fe<Tag>& a) { return a + a; }
+
+// Montgomery -> canonical integer limbs (multiply by the integer 1)
+template <class Tag>
+__host__ __device__ __forceinline__ Fe<Tag> from_mont(const Fe<Tag>& a) {
+    Fe<Tag> one = Fe<Tag>::zero();
+    one.l[0] = 1;
+    return a * one;
+}
+template <class Tag>
+__host__ __device__ __forceinline__ Fe<Tag> to_mont(const Fe<Tag>& a) { return a * fe_r2<Tag>(); }
+
+// a^e for a 256-bit exponent given as 8 u32 limbs (LE); used for inversion (e = p-2)
+template <class Tag>
+__host__ __device__ inline Fe<Tag> fe_pow(const Fe<Tag>& a, const uint32_t* e) {
+    Fe<Tag> acc = fe_one<Tag>();
+    for (int i = 255; i >= 0; --i) {
+        acc = sqr(acc);
+        if ((e[i >> 5] >> (i & 31)) & 1) acc = acc * a;
+    }
+    return acc;
+}
+template <class Tag>
+__host__ __device__ inline Fe<Tag> fe_inv(const Fe<Tag>& a) {  // a^(p-2); 0 -> 0
+    Fe<Tag> e; fe_set_modm2(e);
+    return fe_pow(a, e.l);
+}
+
+// 128-bit vector loads/stores (two per element)
+template <class Tag>
+__device__ __forceinline__ Fe<Tag> fe_load(const Fe<Tag>* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    Fe<Tag> r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+template <class Tag>
+__device__ __forceinline__ Fe<Tag> fe_ldg(const Fe<Tag>* p) {  // read-only path
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    Fe<Tag> r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+template <class Tag>
+__device__ __forceinline__ void fe_store(Fe<Tag>* p, const Fe<Tag>& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+}  // namespace zk

@@ -1,0 +1,261 @@
+// K2 — BN254 G1 multi-scalar multiplication on the device.
+//
+// Replaces halo2curves `best_multiexp` behind `ParamsKZG::{commit,
+// commit_lagrange}` (row a4).  Pippenger with signed c-bit digits:
+//   1. k_msm_count    : scalars Montgomery -> canonical, recode into signed digits, histogram the
+//                       (group, |digit|) keys
+//   2. k_msm_scan     : exclusive prefix sum of the histogram (one CTA per MSM)
+//   3. k_msm_scatter  : recode again and scatter (point index | sign) into bucket-sorted order
+//   4. k_msm_buckets  : one thread per bucket walks its run and accumulates in XYZZ (madd 8M+2S)
+//   5. k_msm_reduce   : sum_b b*B_b per group: per-thread running sums over a bucket segment, a small
+//                       scalar multiple for the segment base, shared-memory tree across the block
+//   6. k_msm_combine  : Horner over windows (plain mode only)
+// Fixed-base ("precomp") mode — the proof hot path, where every commitment uses the same SRS bases —
+// stores T[w][i] = 2^(c*w)*G_i once at SRS registration so all windows share ONE bucket set: the
+// per-MSM cost drops from W*(n madd + 2*nb add) to n*W madd + 2*nb add and step 6 disappears.
+// The group sum is independent of accumulation order and every exceptional case of the addition
+// formulas is handled, so the affine-normalised result is bit-exact against the CPU oracle.
+#include "msm.cuh"
+
+namespace zk {
+
+__host__ __device__ __forceinline__ uint32_t get_bits(const uint32_t* l, unsigned pos, unsigned c) {
+    unsigned word = pos >> 5, shift = pos & 31;
+    if (word >= 8) return 0;
+    uint32_t v = l[word] >> shift;
+    if (shift + c > 32 && word + 1 < 8) v |= l[word + 1] << (32 - shift);
+    return v & ((1u << c) - 1);
+}
+
+// Calls f(w, magnitude in [1, 2^(c-1)], negative) for each non-zero signed digit of canonical scalar s.
+template <class F>
+__host__ __device__ __forceinline__ void for_each_digit(const uint32_t* s, unsigned c, unsigned W, F f) {
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (c - 1);
+    for (unsigned w = 0; w < W; ++w) {
+        uint32_t d = get_bits(s, w * c, c) + carry;
+        if (d > half) { carry = 1; uint32_t mag = (1u << c) - d; if (mag) f(w, mag, true); }
+        else { carry = 0; if (d) f(w, d, false); }
+    }
+}
+
+struct MsmDims { unsigned c, W, G, nb; unsigned precomp; unsigned n; unsigned tstride; };  // tstride: table stride (points per window)
+
+__global__ void k_msm_count(const fr_t* __restrict__ scalars, size_t total, MsmDims D, uint32_t* __restrict__ counts) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    size_t m = idx / D.n;
+    fr_t s = from_mont(fe_load(scalars + idx));
+    uint32_t* cm = counts + m * ((size_t)D.G * D.nb);
+    for_each_digit(s.l, D.c, D.W, [&](unsigned w, uint32_t mag, bool) {
+        unsigned g = D.precomp ? 0 : w;
+        atomicAdd(cm + (size_t)g * D.nb + (mag - 1), 1u);
+    });
+}
+
+// one CTA per MSM; offsets has K+1 entries per MSM
+__global__ void k_msm_scan(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets, unsigned K) {
+    __shared__ uint32_t part[1024];
+    const uint32_t* c = counts + (size_t)blockIdx.x * K;
+    uint32_t* o = offsets + (size_t)blockIdx.x * (K + 1);
+    unsigned per = (K + blockDim.x - 1) / blockDim.x;
+    unsigned lo = threadIdx.x * per, hi = lo + per < K ? lo + per : K;
+    uint32_t sum = 0;
+    for (unsigned i = lo; i < hi; ++i) sum += c[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the per-thread sums
+    for (unsigned d = 1; d < blockDim.x; d <<= 1) {
+        uint32_t v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[threadIdx.x] - sum;
+    for (unsigned i = lo; i < hi; ++i) { o[i] = run; run += c[i]; }
+    if (threadIdx.x == blockDim.x - 1) o[K] = part[threadIdx.x];
+}
+
+__global__ void k_msm_scatter(const fr_t* __restrict__ scalars, size_t total, MsmDims D, uint32_t* __restrict__ counts,
+                              const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    size_t m = idx / D.n;
+    uint32_t i = (uint32_t)(idx - m * D.n);
+    fr_t s = from_mont(fe_load(scalars + idx));
+    const size_t K = (size_t)D.G * D.nb;
+    uint32_t* cm = counts + m * K;
+    const uint32_t* om = offsets + m * (K + 1);
+    uint32_t* em = entries + m * ((size_t)D.n * D.W);
+    for_each_digit(s.l, D.c, D.W, [&](unsigned w, uint32_t mag, bool negative) {
+        unsigned g = D.precomp ? 0 : w;
+        size_t key = (size_t)g * D.nb + (mag - 1);
+        uint32_t pos = atomicSub(cm + key, 1u) - 1;  // leaves the histogram zeroed for the next call
+        uint32_t ref = D.precomp ? w * D.tstride + i : i;
+        em[om[key] + pos] = ref | (negative ? 0x80000000u : 0u);
+    });
+}
+
+__global__ void __launch_bounds__(128) k_msm_buckets(const g1_affine_t* __restrict__ bases, const uint32_t* __restrict__ offsets,
+                                                     const uint32_t* __restrict__ entries, MsmDims D, size_t M,
+                                                     g1_xyzz_t* __restrict__ buckets) {
+    const size_t K = (size_t)D.G * D.nb;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * K) return;
+    size_t m = idx / K, key = idx - m * K;
+    const uint32_t* om = offsets + m * (K + 1);
+    const uint32_t* em = entries + m * ((size_t)D.n * D.W);
+    uint32_t b = om[key], e = om[key + 1];
+    g1_xyzz_t acc = g1_xyzz_t::identity();
+    for (uint32_t t = b; t < e; ++t) {
+        uint32_t ref = em[t];
+        const g1_affine_t* p = bases + (ref & 0x7fffffffu);
+        g1_affine_t q;
+        q.x = fe_ldg(&p->x); q.y = fe_ldg(&p->y);
+        xyzz_madd(acc, q, (ref >> 31) != 0);
+    }
+    g1_xyzz_t* o = buckets + idx;
+    fe_store(&o->x, acc.x); fe_store(&o->y, acc.y); fe_store(&o->zz, acc.zz); fe_store(&o->zzz, acc.zzz);
+}
+
+__device__ __forceinline__ g1_xyzz_t xyzz_load(const g1_xyzz_t* p) {
+    g1_xyzz_t r;
+    r.x = fe_load(&p->x); r.y = fe_load(&p->y); r.zz = fe_load(&p->zz); r.zzz = fe_load(&p->zzz);
+    return r;
+}
+__device__ __forceinline__ void xyzz_store(g1_xyzz_t* p, const g1_xyzz_t& v) {
+    fe_store(&p->x, v.x); fe_store(&p->y, v.y); fe_store(&p->zz, v.zz); fe_store(&p->zzz, v.zzz);
+}
+
+// block per (m, g); T = blockDim.x threads, each owns L = nb/T consecutive buckets
+#define ZK_REDUCE_T 128
+__global__ void __launch_bounds__(ZK_REDUCE_T) k_msm_reduce(const g1_xyzz_t* __restrict__ buckets, MsmDims D,
+                                                            g1_xyzz_t* __restrict__ groups) {
+    __shared__ g1_xyzz_t part[ZK_REDUCE_T];
+    const unsigned T = blockDim.x;
+    const unsigned L = D.nb / T;  // host guarantees T | nb
+    const g1_xyzz_t* B = buckets + (size_t)blockIdx.x * D.nb;
+    unsigned lo = threadIdx.x * L;  // bucket index lo has weight lo+1
+    g1_xyzz_t run = g1_xyzz_t::identity(), acc = g1_xyzz_t::identity();
+    for (unsigned j = L; j-- > 0;) {
+        run = xyzz_add(run, xyzz_load(B + lo + j));
+        acc = xyzz_add(acc, run);
+    }
+    // acc = sum_j (j+1) * B[lo+j]; the segment needs sum_j (lo+j+1) * B = acc + lo * run
+    if (lo) acc = xyzz_add(acc, xyzz_mul_small(run, lo));
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (unsigned s = T >> 1; s > 0; s >>= 1) {
+        if (threadIdx.x < s) part[threadIdx.x] = xyzz_add(part[threadIdx.x], part[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) xyzz_store(groups + blockIdx.x, part[0]);
+}
+
+__global__ void k_msm_combine(const g1_xyzz_t* __restrict__ groups, MsmDims D, size_t M, g1_xyzz_t* __restrict__ out) {
+    size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    g1_xyzz_t acc = g1_xyzz_t::identity();
+    for (unsigned g = D.G; g-- > 0;) {
+        for (unsigned i = 0; i < D.c; ++i) acc = xyzz_dbl(acc);
+        acc = xyzz_add(acc, xyzz_load(groups + m * D.G + g));
+    }
+    xyzz_store(out + m, acc);
+}
+
+__global__ void k_precompute_table(const g1_affine_t* __restrict__ bases, g1_affine_t* __restrict__ table, MsmDims D) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D.n) return;
+    g1_affine_t p;
+    p.x = fe_load(&bases[i].x); p.y = fe_load(&bases[i].y);
+    fe_store(&table[i].x, p.x); fe_store(&table[i].y, p.y);
+    g1_xyzz_t cur = g1_xyzz_t::from_affine(p);
+    for (unsigned w = 1; w < D.W; ++w) {
+        for (unsigned j = 0; j < D.c; ++j) cur = xyzz_dbl(cur);
+        g1_affine_t a = xyzz_to_affine(cur);
+        g1_affine_t* o = table + (size_t)w * D.tstride + i;
+        fe_store(&o->x, a.x); fe_store(&o->y, a.y);
+        cur = g1_xyzz_t::from_affine(a);  // keep ZZ = 1 so later doublings stay cheap and exact
+    }
+}
+
+__global__ void k_normalize(const g1_xyzz_t* __restrict__ in, g1_affine_t* __restrict__ out, size_t m) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    g1_affine_t a = xyzz_to_affine(xyzz_load(in + i));
+    fe_store(&out[i].x, a.x); fe_store(&out[i].y, a.y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+MsmPlan msm_plan(size_t n, bool precomp, unsigned force_c) {
+    MsmPlan p;
+    p.n = n; p.precomp = precomp;
+    unsigned best = 0; double best_cost = 0;
+    for (unsigned c = 2; c <= 16; ++c) {
+        unsigned W = 254 / c + 1;
+        double nb = (double)(1u << (c - 1));
+        double cost = precomp ? (double)n * W * 10 + nb * 28 : W * ((double)n * 10 + nb * 28);
+        if (!best || cost < best_cost) { best = c; best_cost = cost; }
+    }
+    p.c = force_c ? force_c : best;
+    ZK_REQUIRE(p.c >= 2 && p.c <= 16, "msm: window must be in [2,16]");
+    p.W = 254 / p.c + 1;
+    p.nb = 1u << (p.c - 1);
+    p.G = precomp ? 1 : p.W;
+    ZK_REQUIRE(n * p.W < (1ull << 31), "msm: n*W must fit 31 bits");
+    return p;
+}
+
+void MsmWorkspace::ensure(const MsmPlan& p, size_t M) {
+    size_t K = p.K();
+    if (counts.n < M * K) {
+        counts.alloc(M * K);
+        ZK_CUDA(cudaMemset(counts.p, 0, counts.bytes()));
+    }
+    offsets.ensure(M * (K + 1));
+    entries.ensure(M * p.entries_per_msm());
+    buckets.ensure(M * K);
+    groups.ensure(M * p.G);
+}
+
+static MsmDims dims_of(const MsmPlan& p) {
+    MsmDims D; D.c = p.c; D.W = p.W; D.G = p.G; D.nb = p.nb; D.precomp = p.precomp ? 1 : 0; D.n = (unsigned)p.n; D.tstride = (unsigned)(p.tstride ? p.tstride : p.n);
+    return D;
+}
+
+void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_bases, size_t M, g1_xyzz_t* d_out,
+             MsmWorkspace& ws, cudaStream_t st) {
+    if (M == 0) return;
+    ZK_REQUIRE(plan.n > 0 && plan.n < (1ull << 31), "msm: bad n");
+    ws.ensure(plan, M);
+    MsmDims D = dims_of(plan);
+    const size_t K = plan.K();
+    const size_t total = M * plan.n;
+    ZK_REQUIRE(K <= (1u << 30), "msm: too many buckets");
+    ZK_LAUNCH(k_msm_count, ceil_div(total, 256), 256, 0, st, d_scalars, total, D, ws.counts.p);
+    unsigned scan_threads = K >= 1024 ? 1024 : 32;
+    while (scan_threads < K && scan_threads < 1024) scan_threads <<= 1;
+    ZK_LAUNCH(k_msm_scan, (unsigned)M, scan_threads, 0, st, ws.counts.p, ws.offsets.p, (unsigned)K);
+    ZK_LAUNCH(k_msm_scatter, ceil_div(total, 256), 256, 0, st, d_scalars, total, D, ws.counts.p, ws.offsets.p, ws.entries.p);
+    ZK_LAUNCH(k_msm_buckets, ceil_div(M * K, 128), 128, 0, st, d_bases, ws.offsets.p, ws.entries.p, D, M, ws.buckets.p);
+    unsigned T = plan.nb < ZK_REDUCE_T ? plan.nb : ZK_REDUCE_T;
+    g1_xyzz_t* groups = plan.precomp ? d_out : ws.groups.p;
+    ZK_LAUNCH(k_msm_reduce, (unsigned)(M * plan.G), T, 0, st, ws.buckets.p, D, groups);
+    if (!plan.precomp) {
+        ZK_LAUNCH(k_msm_combine, ceil_div(M, 64), 64, 0, st, ws.groups.p, D, M, d_out);
+    }
+}
+
+void msm_precompute_table(const MsmPlan& plan, const g1_affine_t* d_bases, g1_affine_t* d_table, cudaStream_t st) {
+    MsmDims D = dims_of(plan);
+    ZK_LAUNCH(k_precompute_table, ceil_div(plan.n, 64), 64, 0, st, d_bases, d_table, D);
+}
+
+void g1_normalize(const g1_xyzz_t* d_in, g1_affine_t* d_out, size_t m, cudaStream_t st) {
+    if (!m) return;
+    ZK_LAUNCH(k_normalize, ceil_div(m, 64), 64, 0, st, d_in, d_out, m);
+}
+
+}  // namespace zk

@@ -1,0 +1,39 @@
+// Internal interface of the MSM module (msm.cu).
+#pragma once
+#include "common.cuh"
+#include "ec.cuh"
+
+namespace zk {
+
+// Pippenger layout.  Signed c-bit digits, W = 254/c + 1 windows, nb = 2^(c-1) buckets per group.
+//   plain   : G = W bucket groups (one per window), entries index the caller's bases directly
+//   precomp : G = 1 — every window shares one bucket set because the bases carry a table
+//             T[w][i] = 2^(c*w) * base[i] (fixed-base SRS path); entries index w*n + i
+struct MsmPlan {
+    unsigned c = 0, W = 0, G = 0, nb = 0;
+    bool precomp = false;
+    size_t n = 0;        // scalars per MSM
+    size_t tstride = 0;  // precomp: points per window in the table (0 = n)
+    size_t K() const { return (size_t)G * nb; }            // buckets per MSM
+    size_t entries_per_msm() const { return n * W; }
+};
+MsmPlan msm_plan(size_t n, bool precomp, unsigned force_c = 0);
+
+struct MsmWorkspace {
+    DevBuf<uint32_t> counts;    // M * K      (zero between calls)
+    DevBuf<uint32_t> offsets;   // M * (K+1)
+    DevBuf<uint32_t> entries;   // M * n * W
+    DevBuf<g1_xyzz_t> buckets;  // M * K
+    DevBuf<g1_xyzz_t> groups;   // M * G
+    void ensure(const MsmPlan& p, size_t M);
+};
+
+// out[m] = sum_i scalars[m*n + i] * bases[i]  (XYZZ, not normalised).  Scalars in Montgomery form.
+void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_bases_or_table, size_t M,
+             g1_xyzz_t* d_out, MsmWorkspace& ws, cudaStream_t st);
+// table[w*n + i] = 2^(c*w) * bases[i], affine
+void msm_precompute_table(const MsmPlan& plan, const g1_affine_t* d_bases, g1_affine_t* d_table, cudaStream_t st);
+// affine normalisation of m points (one inversion each)
+void g1_normalize(const g1_xyzz_t* d_in, g1_affine_t* d_out, size_t m, cudaStream_t st);
+
+}  // namespace zk

@@ -1,0 +1,293 @@
+// K3/K4 — BN254 Fr NTT on the device.
+//
+// Replaces halo2curves `best_fft::<Fr,Fr>` (natural order in and out) and the
+// `EvaluationDomain::{coeff_to_extended, extended_to_coeff}` wrappers around it (row a6).
+//
+// Structure: a transform of N = 2^log_N points is one or two "tile passes".  A tile pass loads
+// C interleaved sequences of m = 2^log_m points into shared memory (limb-major planes, bit-reversed
+// and XOR-swizzled so both the bit-reversed fill and the butterfly sweeps are bank-conflict free),
+// runs log_m radix-2 DIT stages there, and stores.
+//   * N <= 2^12: one pass, the whole polynomial lives in one CTA's shared memory (128 KB at 2^12).
+//   * larger N = n1*n2 (four-step): pass 1 transforms columns (stride n2, C adjacent columns per tile so
+//     every global access is C*32 contiguous bytes), multiplies by w_N^(i2*k1), writes in place to a
+//     scratch buffer; pass 2 transforms rows (contiguous) and writes transposed (k1 + n1*k2), again C
+//     rows per tile so the strided stores are C*32-byte segments.  Natural order out, no separate
+//     transpose or bit-reversal pass.
+// Coset scaling (zeta^(i mod 3), zeta^3 = 1), zero-padding and the 1/N factor of inverse transforms
+// are fused into the load / store of the passes.
+#include "ntt.cuh"
+#include <map>
+#include <mutex>
+#include <array>
+
+namespace zk {
+
+struct NttPass {
+    const fr_t* in;
+    fr_t* out;
+    const fr_t* tw;  // w_N^i, i < N/2
+    unsigned log_N, log_m, log_C, swz_q;
+    unsigned tiles_per_poly;
+    size_t in_poly_stride, out_poly_stride;
+    size_t in_tile_stride, in_sj, in_sc;
+    size_t out_tile_stride, out_sj, out_sc;
+    size_t in_valid;     // elements >= in_valid (index within the polynomial) read as zero
+    int c_fastest_in, c_fastest_out;
+    int post_twiddle;    // multiply (k, c) by w_N^((tile*C + c) * k)
+    int pre_coset;       // multiply input element i by cs1 (i%3==1) / cs2 (i%3==2)
+    int post_coset;      // same on output index
+    int has_scale;
+    fr_t scale, cs1, cs2;
+};
+
+__device__ __forceinline__ unsigned swz(unsigned p, unsigned log_m, unsigned q) {
+    // fold the top q bits (bit-reversed) into the low q bits
+    if (q == 0) return p;
+    unsigned top = p >> (log_m - q);
+    return p ^ (__brev(top) >> (32 - q));
+}
+
+__device__ __forceinline__ fr_t smem_ld(const uint32_t* s, unsigned plane, unsigned w) {
+    fr_t v;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) v.l[l] = s[l * plane + w];
+    return v;
+}
+__device__ __forceinline__ void smem_st(uint32_t* s, unsigned plane, unsigned w, const fr_t& v) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) s[l * plane + w] = v.l[l];
+}
+
+__global__ void __launch_bounds__(1024, 1) k_ntt_tile(const NttPass P) {
+    extern __shared__ uint32_t smem[];
+    const unsigned log_m = P.log_m, log_C = P.log_C, q = P.swz_q;
+    const unsigned m = 1u << log_m, C = 1u << log_C, total = m << log_C;
+    const unsigned tile = blockIdx.x % P.tiles_per_poly;
+    const size_t poly = blockIdx.x / P.tiles_per_poly;
+    const fr_t* in = P.in + poly * P.in_poly_stride + (size_t)tile * P.in_tile_stride;
+    fr_t* out = P.out + poly * P.out_poly_stride + (size_t)tile * P.out_tile_stride;
+
+    for (unsigned e = threadIdx.x; e < total; e += blockDim.x) {
+        unsigned c, j;
+        if (P.c_fastest_in) { c = e & (C - 1); j = e >> log_C; } else { j = e & (m - 1); c = e >> log_m; }
+        size_t off = (size_t)j * P.in_sj + (size_t)c * P.in_sc;
+        size_t gi = (size_t)tile * P.in_tile_stride + off;  // index within the polynomial
+        fr_t v = gi < P.in_valid ? fe_load(in + off) : fr_t::zero();
+        if (P.pre_coset) {
+            unsigned r3 = (unsigned)(gi % 3);
+            if (r3 == 1) v = v * P.cs1; else if (r3 == 2) v = v * P.cs2;
+        }
+        unsigned p = swz(__brev(j) >> (32 - log_m), log_m, q);
+        smem_st(smem, total, (p << log_C) | c, v);
+    }
+    __syncthreads();
+
+    for (unsigned s = 0; s < log_m; ++s) {
+        const unsigned half = 1u << s;
+        for (unsigned e = threadIdx.x; e < (total >> 1); e += blockDim.x) {
+            unsigned c = e & (C - 1), b = e >> log_C;
+            unsigned jj = b & (half - 1);
+            unsigned i = ((b >> s) << (s + 1)) | jj;
+            unsigned lo = (swz(i, log_m, q) << log_C) | c, hi = (swz(i + half, log_m, q) << log_C) | c;
+            fr_t a = smem_ld(smem, total, lo), bb = smem_ld(smem, total, hi);
+            if (jj) bb = bb * fe_ldg(P.tw + ((size_t)jj << (P.log_N - s - 1)));
+            smem_st(smem, total, lo, a + bb);
+            smem_st(smem, total, hi, a - bb);
+        }
+        __syncthreads();
+    }
+
+    const size_t halfN = (size_t)1 << (P.log_N - 1);
+    for (unsigned e = threadIdx.x; e < total; e += blockDim.x) {
+        unsigned c, k;
+        if (P.c_fastest_out) { c = e & (C - 1); k = e >> log_C; } else { k = e & (m - 1); c = e >> log_m; }
+        fr_t v = smem_ld(smem, total, (swz(k, log_m, q) << log_C) | c);
+        if (P.post_twiddle) {
+            size_t ex = ((size_t)tile * C + c) * k;
+            if (ex) {
+                if (ex >= halfN) v = neg(v * fe_ldg(P.tw + (ex - halfN)));
+                else v = v * fe_ldg(P.tw + ex);
+            }
+        }
+        size_t off = (size_t)k * P.out_sj + (size_t)c * P.out_sc;
+        if (P.post_coset) {
+            size_t gi = (size_t)tile * P.out_tile_stride + off;
+            unsigned r3 = (unsigned)(gi % 3);
+            if (r3 == 1) v = v * P.cs1; else if (r3 == 2) v = v * P.cs2;
+        }
+        if (P.has_scale) v = v * P.scale;
+        fe_store(out + off, v);
+    }
+}
+
+// tw[i] = w^i for i < count, from pows[b] = w^(2^b)
+__global__ void k_twiddles(fr_t* tw, size_t count, const fr_t* pows, unsigned nbits) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    fr_t acc = fe_one<FrTag>();
+    for (unsigned b = 0; b < nbits; ++b)
+        if ((i >> b) & 1) acc = acc * fe_ldg(pows + b);
+    fe_store(tw + i, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+fr_t fr_from_limbs(const uint32_t* l) { fr_t r; for (int i = 0; i < 8; ++i) r.l[i] = l[i]; return r; }
+fr_t fr_from_u64(uint64_t v) {
+    fr_t r = fr_t::zero(); r.l[0] = (uint32_t)v; r.l[1] = (uint32_t)(v >> 32);
+    return to_mont(r);
+}
+fr_t fr_pow_u64(fr_t b, uint64_t e) {
+    fr_t acc = fe_one<FrTag>();
+    while (e) { if (e & 1) acc = acc * b; b = sqr(b); e >>= 1; }
+    return acc;
+}
+fr_t fr_omega(unsigned log_n) {  // ROOT_OF_UNITY^(2^(28-log_n)) — EvaluationDomain::new
+    fr_t w = fr_from_limbs(fr_consts::ROOT_OF_UNITY);
+    for (unsigned i = log_n; i < fr_consts::S; ++i) w = sqr(w);
+    return w;
+}
+fr_t fr_omega_inv(unsigned log_n) {
+    fr_t w = fr_from_limbs(fr_consts::ROOT_OF_UNITY_INV);
+    for (unsigned i = log_n; i < fr_consts::S; ++i) w = sqr(w);
+    return w;
+}
+fr_t fr_pow2_inv(unsigned log_n) {  // (2^log_n)^-1
+    return fr_pow_u64(fr_from_limbs(fr_consts::TWO_INV), log_n);
+}
+
+namespace {
+struct TwKey {
+    int dev; unsigned log_n; std::array<uint32_t, 8> w;
+    bool operator<(const TwKey& o) const {
+        if (dev != o.dev) return dev < o.dev;
+        if (log_n != o.log_n) return log_n < o.log_n;
+        return w < o.w;
+    }
+};
+std::mutex g_tw_mu;
+std::map<TwKey, DevBuf<fr_t>> g_tw;
+}  // namespace
+
+const fr_t* ntt_twiddles(unsigned log_n, const fr_t& omega, cudaStream_t st) {
+    int dev; ZK_CUDA(cudaGetDevice(&dev));
+    TwKey key; key.dev = dev; key.log_n = log_n;
+    for (int i = 0; i < 8; ++i) key.w[i] = omega.l[i];
+    std::lock_guard<std::mutex> lk(g_tw_mu);
+    auto it = g_tw.find(key);
+    if (it != g_tw.end()) return it->second.p;
+    size_t count = log_n ? ((size_t)1 << (log_n - 1)) : 1;
+    std::vector<fr_t> pows(log_n ? log_n : 1);
+    fr_t w = omega;
+    for (unsigned b = 0; b < pows.size(); ++b) { pows[b] = w; w = sqr(w); }
+    DevBuf<fr_t> d_pows(pows.size()), d_tw(count);
+    ZK_CUDA(cudaMemcpyAsync(d_pows.p, pows.data(), pows.size() * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+    ZK_LAUNCH(k_twiddles, ceil_div(count, 256), 256, 0, st, d_tw.p, count, d_pows.p, log_n ? log_n - 1 : 0);
+    ZK_CUDA(cudaStreamSynchronize(st));
+    const fr_t* p = d_tw.p;
+    g_tw.emplace(key, std::move(d_tw));
+    return p;
+}
+void ntt_clear_cache() {
+    std::lock_guard<std::mutex> lk(g_tw_mu);
+    g_tw.clear();
+}
+
+static void launch_pass(const NttPass& P, size_t batch, cudaStream_t st) {
+    unsigned total = 1u << (P.log_m + P.log_C);
+    size_t smem = (size_t)total * 32;
+    unsigned threads = total / 2 < 1024 ? (total / 2 < 32 ? 32 : total / 2) : 1024;
+    static std::mutex mu; static std::map<int, size_t> cur;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        int dev; ZK_CUDA(cudaGetDevice(&dev));
+        if (smem > 48 * 1024 && cur[dev] < smem) {
+            ZK_CUDA(cudaFuncSetAttribute(k_ntt_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            cur[dev] = 200 * 1024;
+        }
+    }
+    size_t blocks = batch * P.tiles_per_poly;
+    ZK_REQUIRE(blocks < (1ull << 31), "ntt: grid too large");
+    ZK_LAUNCH(k_ntt_tile, (unsigned)blocks, threads, smem, st, P);
+}
+
+static unsigned pick_swz(unsigned log_m, unsigned log_C) {
+    unsigned q = log_C >= 5 ? 0 : 5 - log_C;
+    if (q > log_m / 2) q = log_m / 2;
+    return q;
+}
+
+size_t ntt_scratch_elems(unsigned log_n, size_t batch) {
+    return log_n > NTT_SINGLE_PASS_MAX_LOG ? batch << log_n : 0;
+}
+
+void ntt_run(const NttJob& J, cudaStream_t st) {
+    const unsigned log_N = J.log_n;
+    ZK_REQUIRE(log_N <= 26, "ntt: log_n too large");
+    const size_t N = (size_t)1 << log_N;
+    if (log_N == 0) {
+        ZK_REQUIRE(J.in == J.out, "ntt: size-1 transform must be in place");
+        return;
+    }
+    const fr_t* tw = ntt_twiddles(log_N, J.omega, st);
+    NttPass P;
+    memset(&P, 0, sizeof P);
+    P.tw = tw; P.log_N = log_N;
+    P.in_poly_stride = J.in_stride ? J.in_stride : N;
+    P.out_poly_stride = J.out_stride ? J.out_stride : N;
+    P.in_valid = J.in_valid ? J.in_valid : N;
+    fr_t one = fe_one<FrTag>();
+    P.cs1 = J.pre_coset ? J.cs1 : (J.post_coset ? J.cs1 : one);
+    P.cs2 = J.pre_coset ? J.cs2 : (J.post_coset ? J.cs2 : one);
+    if (log_N <= NTT_SINGLE_PASS_MAX_LOG) {
+        P.in = J.in; P.out = J.out;
+        P.log_m = log_N; P.log_C = 0; P.swz_q = pick_swz(log_N, 0);
+        P.tiles_per_poly = 1;
+        P.in_sj = 1; P.in_sc = 0; P.out_sj = 1; P.out_sc = 0;
+        P.c_fastest_in = 0; P.c_fastest_out = 0;
+        P.pre_coset = J.pre_coset; P.post_coset = J.post_coset;
+        P.has_scale = J.has_scale; P.scale = J.scale;
+        launch_pass(P, J.batch, st);
+        return;
+    }
+    ZK_REQUIRE(J.scratch != nullptr, "ntt: scratch buffer required for two-pass transforms");
+    const unsigned log_n1 = log_N / 2, log_n2 = log_N - log_n1;
+    const size_t n1 = (size_t)1 << log_n1, n2 = (size_t)1 << log_n2;
+    ZK_REQUIRE(log_n2 <= 12, "ntt: log_n too large for two passes");
+    // tile width: 8 columns (256 B segments) unless the tile would exceed ~128 KB
+    auto pick_c = [](unsigned log_m) { unsigned lc = 3; while (log_m + lc > 12) --lc; return lc; };
+    // pass 1: columns, in -> scratch (same layout), twiddle by w_N^(i2*k1)
+    {
+        NttPass A = P;
+        A.in = J.in; A.out = J.scratch;
+        A.out_poly_stride = N;
+        A.log_m = log_n1; A.log_C = pick_c(log_n1); A.swz_q = pick_swz(A.log_m, A.log_C);
+        unsigned C = 1u << A.log_C;
+        A.tiles_per_poly = (unsigned)(n2 >> A.log_C);
+        A.in_tile_stride = C; A.in_sj = n2; A.in_sc = 1;
+        A.out_tile_stride = C; A.out_sj = n2; A.out_sc = 1;
+        A.c_fastest_in = 1; A.c_fastest_out = 1;
+        A.post_twiddle = 1;
+        A.pre_coset = J.pre_coset; A.post_coset = 0; A.has_scale = 0;
+        launch_pass(A, J.batch, st);
+    }
+    // pass 2: rows of the scratch, written transposed to out
+    {
+        NttPass B = P;
+        B.in = J.scratch; B.out = J.out;
+        B.in_poly_stride = N; B.in_valid = N;
+        B.log_m = log_n2; B.log_C = pick_c(log_n2); B.swz_q = pick_swz(B.log_m, B.log_C);
+        unsigned C = 1u << B.log_C;
+        B.tiles_per_poly = (unsigned)(n1 >> B.log_C);
+        B.in_tile_stride = (size_t)C * n2; B.in_sj = 1; B.in_sc = n2;
+        B.out_tile_stride = C; B.out_sj = n1; B.out_sc = 1;
+        B.c_fastest_in = 0; B.c_fastest_out = 1;
+        B.post_twiddle = 0;
+        B.pre_coset = 0; B.post_coset = J.post_coset; B.has_scale = J.has_scale; B.scale = J.scale;
+        // inner transforms of length n2 use w_{n2} = w_N^(n1): handled by the (log_N - s - 1) shift
+        launch_pass(B, J.batch, st);
+    }
+}
+
+}  // namespace zk

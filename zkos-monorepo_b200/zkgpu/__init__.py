@@ -1,0 +1,200 @@
+"""zkgpu — Python host mirror of the reference-facing prover interface, over libzkgpu's C ABI.
+
+The reference's host side is Rust (no cargo in this image), so the product's host logic lives in C++
+inside ``libzkgpu.so``; this module is only the thin ctypes binding used by the tests and the
+benchmark.  Names follow the upstream halo2 / halo2curves API that Shielder reaches through
+``shielder_circuits::generate_proof`` (/root/reference/crates/shielder_bindings/src/circuits/mod.rs:103-111):
+
+    best_multiexp(coeffs, bases)          halo2curves::msm::best_multiexp
+    best_fft(a, omega, log_n)             halo2curves::fft::best_fft
+    ParamsKZG(k, g, g_lagrange).commit / .commit_lagrange      halo2_proofs poly/kzg/commitment.rs
+    EvaluationDomain(j, k).{lagrange_to_coeff, coeff_to_lagrange, coeff_to_extended, extended_to_coeff}
+    g_to_lagrange(g, k)                   ParamsKZG::from_parts(.., None, ..)  (powers-of-tau/lib.rs:71)
+
+Arrays are numpy uint64 in the Rust memory layout: field elements (..., 4) Montgomery limbs,
+affine points (..., 8).  There is NO CPU fallback: if the CUDA library is missing or no GPU is
+visible, every call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libzkgpu.so")
+_lib = None
+
+
+class ZkGpuError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads libzkgpu.so (built in-tree by __graft_entry__.build()).  Fails loudly if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ZkGpuError("libzkgpu.so not built (%s); run __graft_entry__.build() — there is no CPU fallback" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.zkgpu_last_error.restype = C.c_char_p
+        _lib.zkgpu_launch_count.restype = C.c_uint64
+    return _lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise ZkGpuError("libzkgpu error %d: %s" % (rc, lib().zkgpu_last_error().decode()))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def init(device=0):
+    _chk(lib().zkgpu_init(int(device)))
+
+
+def shutdown():
+    lib().zkgpu_shutdown()
+
+
+def launch_count():
+    return int(lib().zkgpu_launch_count())
+
+
+def _jac_to_affine(j):
+    """normalised Jacobian (x, y, 1) / (0, 1, 0) -> affine (x, y) / (0, 0)"""
+    out = np.zeros(8, dtype=np.uint64)
+    if j[8:].any():
+        out[:] = j[:8]
+    return out
+
+
+def best_multiexp(coeffs, bases):
+    """sum_i coeffs[i] * bases[i]; returns the affine-normalised point (8 u64)."""
+    coeffs, bases = _u64(coeffs), _u64(bases)
+    n = coeffs.size // 4
+    if bases.size // 8 != n:
+        raise ZkGpuError("best_multiexp: coeffs.len() != bases.len()")  # upstream assert_eq!
+    out = np.zeros(12, dtype=np.uint64)
+    _chk(lib().zkgpu_msm_g1(_p(coeffs), _p(bases), C.c_size_t(n), _p(out)))
+    return _jac_to_affine(out)
+
+
+def best_fft(a, omega, log_n, batch=1):
+    """In-place semantics of halo2curves best_fft; returns the transformed copy."""
+    a = np.array(a, dtype=np.uint64, copy=True)
+    omega = _u64(omega)
+    if a.size != 4 * batch << log_n:
+        raise ZkGpuError("best_fft: a.len() != 1 << log_n")
+    _chk(lib().zkgpu_ntt_fr_batch(_p(a), _p(omega), C.c_uint32(log_n), C.c_size_t(batch)))
+    return a
+
+
+def g_to_lagrange(g, k):
+    g = _u64(g)
+    out = np.empty((1 << k, 8), dtype=np.uint64)
+    _chk(lib().zkgpu_g_to_lagrange(_p(g), C.c_uint32(k), _p(out)))
+    return out
+
+
+def fft_g1(points_jacobian, omega, log_n):
+    pts = np.array(points_jacobian, dtype=np.uint64, copy=True)
+    _chk(lib().zkgpu_fft_g1(_p(pts), _p(_u64(omega)), C.c_uint32(log_n)))
+    return pts
+
+
+class ParamsKZG:
+    """Device-resident SRS: ParamsKZG::{commit, commit_lagrange}; `Blind` is ignored by KZG."""
+
+    def __init__(self, k, g, g_lagrange):
+        self.k, self.n = int(k), 1 << int(k)
+        g, g_lagrange = _u64(g), _u64(g_lagrange)
+        if g.size != 8 * self.n or g_lagrange.size != 8 * self.n:
+            raise ZkGpuError("ParamsKZG: g / g_lagrange must hold 2^k points")
+        h = C.c_uint64(0)
+        _chk(lib().zkgpu_srs_register(_p(g), _p(g_lagrange), C.c_uint32(self.k), C.byref(h)))
+        self.handle = h.value
+
+    def _msm(self, basis, scalars):
+        scalars = _u64(scalars)
+        n = scalars.size // 4
+        out = np.zeros(12, dtype=np.uint64)
+        _chk(lib().zkgpu_msm_g1_srs(C.c_uint64(self.handle), basis, _p(scalars), C.c_size_t(n), _p(out)))
+        return _jac_to_affine(out)
+
+    def commit(self, poly_coeffs, blind=None):
+        return self._msm(0, poly_coeffs)
+
+    def commit_lagrange(self, poly_values, blind=None):
+        return self._msm(1, poly_values)
+
+    def commit_batch(self, basis, scalars, n):
+        """m commitments over the same basis in one call; scalars (m, n, 4) -> (m, 8) affine"""
+        scalars = _u64(scalars)
+        m = scalars.size // (4 * n)
+        out = np.empty((m, 8), dtype=np.uint64)
+        _chk(lib().zkgpu_msm_g1_srs_batch(C.c_uint64(self.handle), basis, _p(scalars), C.c_size_t(n), C.c_size_t(m), _p(out)))
+        return out
+
+    def commit_batch_dev(self, basis, d_scalars_ptr, n, m, d_out_ptr, stream=0):
+        _chk(lib().zkgpu_msm_g1_srs_batch_dev(C.c_uint64(self.handle), basis, C.c_void_p(d_scalars_ptr), C.c_size_t(n),
+                                              C.c_size_t(m), C.c_void_p(d_out_ptr), C.c_void_p(stream)))
+
+    def release(self):
+        if self.handle:
+            lib().zkgpu_srs_release(C.c_uint64(self.handle))
+            self.handle = 0
+
+
+class EvaluationDomain:
+    """halo2_proofs poly/domain.rs EvaluationDomain::new(j, k)."""
+
+    def __init__(self, j, k):
+        self.j, self.k = int(j), int(k)
+        self.n = 1 << self.k
+        self.quotient_poly_degree = self.j - 1
+        self.extended_k = self.k
+        while (1 << self.extended_k) < self.n * self.quotient_poly_degree:
+            self.extended_k += 1
+
+    def extended_len(self):
+        return 1 << self.extended_k
+
+    def _domain_ntt(self, a, inverse):
+        a = np.array(a, dtype=np.uint64, copy=True)
+        m = a.size // (4 * self.n)
+        if m * 4 * self.n != a.size:
+            raise ZkGpuError("polynomial length must be a multiple of 2^k")
+        _chk(lib().zkgpu_domain_ntt_fr(_p(a), C.c_uint32(self.k), int(inverse), C.c_size_t(m)))
+        return a
+
+    def lagrange_to_coeff(self, a):
+        return self._domain_ntt(a, 1)
+
+    def coeff_to_lagrange(self, a):
+        return self._domain_ntt(a, 0)
+
+    def coeff_to_extended(self, a):
+        a = _u64(a)
+        if a.size != 4 * self.n:
+            raise ZkGpuError("coeff_to_extended: expected 2^k coefficients")
+        out = np.empty((self.extended_len(), 4), dtype=np.uint64)
+        _chk(lib().zkgpu_coset_ntt_fr(_p(a), C.c_uint32(self.k), C.c_uint32(self.extended_k), _p(out)))
+        return out
+
+    def extended_to_coeff(self, a):
+        a = np.array(a, dtype=np.uint64, copy=True)
+        if a.size != 4 * self.extended_len():
+            raise ZkGpuError("extended_to_coeff: expected 2^extended_k evaluations")
+        _chk(lib().zkgpu_coset_intt_fr(_p(a), C.c_uint32(self.k), C.c_uint32(self.extended_k), C.c_uint32(self.quotient_poly_degree)))
+        return a.reshape(-1, 4)[: self.n * self.quotient_poly_degree]
+
+
+def ntt_batch_dev(d_ptr, omega, log_n, m, d_scratch_ptr=0, stream=0):
+    _chk(lib().zkgpu_ntt_fr_batch_dev(C.c_void_p(d_ptr), _p(_u64(omega)), C.c_uint32(log_n), C.c_size_t(m),
+                                      C.c_void_p(d_scratch_ptr), C.c_void_p(stream)))
