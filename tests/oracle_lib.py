@@ -181,3 +181,84 @@ def g2_on_curve(q):
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 RAW11 = os.path.join(GOLDEN, "ppot_0080_11_raw.bin")
+
+
+# ---- PLONK prover / verifier (oracle/plonk.hpp) ------------------------------------------------
+class OracleBackend:
+    """Field backend for zkgpu.circuits backed by the CPU oracle (tests only)."""
+
+    @staticmethod
+    def random(seed, count):
+        return random_fr(seed, count)
+
+    @staticmethod
+    def const(v):
+        import pyref
+        return to_mont(0, pyref.int_to_limbs([v % pyref.R_MOD]))[0]
+
+    @staticmethod
+    def mul(a, b):
+        return field_op(0, 0, a, b).reshape(-1, 4)
+
+    @staticmethod
+    def add(a, b):
+        return field_op(0, 1, a, b).reshape(-1, 4)
+
+    @staticmethod
+    def sub(a, b):
+        return field_op(0, 2, a, b).reshape(-1, 4)
+
+
+def downsized_srs(k, raw=None):
+    """ParamsKZG::downsize(k) of the k=11 fixture: truncate g, recompute g_lagrange (oracle)."""
+    raw = raw or srs_read(RAW11, 0)
+    assert k <= raw["k"]
+    if k == raw["k"]:
+        return dict(raw)
+    g = raw["g"][: 1 << k].copy()
+    return dict(k=k, g=g, g_lagrange=g_to_lagrange(g, k, threads=8), g2=raw["g2"], s_g2=raw["s_g2"])
+
+
+class PlonkOracle:
+    def __init__(self, blob: bytes, srs, threads=1):
+        self.h = C.c_void_p()
+        g2s = np.concatenate([srs["g2"], srs["s_g2"]]).astype(np.uint64)
+        g, gl = np.ascontiguousarray(srs["g"]), np.ascontiguousarray(srs["g_lagrange"])
+        _chk(lib().orc_plonk_new(blob, C.c_size_t(len(blob)), srs["k"], _p(g), _p(gl), _p(g2s), threads, C.byref(self.h)))
+        info = np.zeros(16, dtype=np.uint64)
+        _chk(lib().orc_plonk_info(self.h, _p(info)))
+        (self.k, self.n, self.num_advice, self.num_fixed, self.degree, self.blinding_factors, self.num_perm_sets,
+         self.num_quotients, self.num_evals, self.proof_len, self.extended_k) = [int(x) for x in info[:11]]
+
+    def vk(self, num_perm_cols):
+        fc = np.zeros((self.num_fixed, 8), dtype=np.uint64)
+        pc = np.zeros((num_perm_cols, 8), dtype=np.uint64)
+        dg = np.zeros(4, dtype=np.uint64)
+        _chk(lib().orc_plonk_vk(self.h, _p(fc), _p(pc), _p(dg)))
+        return fc, pc, dg
+
+    def check_witness(self, advice, instance):
+        ok = C.c_int(0)
+        advice, instance = np.ascontiguousarray(advice), np.ascontiguousarray(instance)
+        _chk(lib().orc_plonk_check_witness(self.h, _p(advice), _p(instance), C.c_size_t(instance.size // 4), C.byref(ok)))
+        return bool(ok.value), lib().orc_last_error().decode()
+
+    def prove(self, advice, instance, seed):
+        advice, instance = np.ascontiguousarray(advice), np.ascontiguousarray(instance)
+        proof = C.create_string_buffer(self.proof_len)
+        stats = np.zeros(3, dtype=np.uint64)
+        _chk(lib().orc_plonk_prove(self.h, _p(advice), _p(instance), C.c_size_t(instance.size // 4), C.c_uint64(seed), proof, _p(stats)))
+        self.last_stats = dict(msm=int(stats[0]), ntt=int(stats[1]), ext_ntt=int(stats[2]))
+        return proof.raw
+
+    def verify(self, proof: bytes, instance):
+        ok = C.c_int(0)
+        instance = np.ascontiguousarray(instance)
+        _chk(lib().orc_plonk_verify(self.h, proof, C.c_size_t(len(proof)), _p(instance), C.c_size_t(instance.size // 4), C.byref(ok)))
+        return bool(ok.value)
+
+    def __del__(self):
+        try:
+            lib().orc_plonk_free(self.h)
+        except Exception:
+            pass

@@ -23,9 +23,11 @@ __global__ void k_imad(uint32_t* out, uint32_t seed) {
                          "mad.hi.u32 %4, %4, %8, %9; mad.hi.u32 %5, %5, %8, %9; mad.hi.u32 %6, %6, %8, %9; mad.hi.u32 %7, %7, %8, %9;"
                          : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7) : "r"(b), "r"(a));
         } else {
-            asm volatile("mad.wide.u32 %0, %8, %9, %0; mad.wide.u32 %1, %8, %9, %1; mad.wide.u32 %2, %8, %9, %2; mad.wide.u32 %3, %8, %9, %3;"
-                         "mad.wide.u32 %4, %8, %9, %4; mad.wide.u32 %5, %8, %9, %5; mad.wide.u32 %6, %8, %9, %6; mad.wide.u32 %7, %8, %9, %7;"
-                         : "+l"(w0), "+l"(w1), "+l"(w2), "+l"(w3), "+l"(w4), "+l"(w5), "+l"(w6), "+l"(w7) : "r"(b), "r"(a));
+            // multiplicand = low half of the running accumulator, so the product cannot be hoisted
+            asm volatile("mad.wide.u32 %0, %8, %16, %0; mad.wide.u32 %1, %9, %16, %1; mad.wide.u32 %2, %10, %16, %2; mad.wide.u32 %3, %11, %16, %3;"
+                         "mad.wide.u32 %4, %12, %16, %4; mad.wide.u32 %5, %13, %16, %5; mad.wide.u32 %6, %14, %16, %6; mad.wide.u32 %7, %15, %16, %7;"
+                         : "+l"(w0), "+l"(w1), "+l"(w2), "+l"(w3), "+l"(w4), "+l"(w5), "+l"(w6), "+l"(w7)
+                         : "r"((uint32_t)w0), "r"((uint32_t)w1), "r"((uint32_t)w2), "r"((uint32_t)w3), "r"((uint32_t)w4), "r"((uint32_t)w5), "r"((uint32_t)w6), "r"((uint32_t)w7), "r"(b));
         }
     }
     uint32_t r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7 ^ (uint32_t)(w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7) ^ (uint32_t)((w0 ^ w7) >> 32);
