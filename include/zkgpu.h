@@ -80,10 +80,58 @@ int zkgpu_fft_g1(uint64_t* points_jacobian, const uint64_t omega[4], uint32_t lo
 /* g_to_lagrange(g, k): n^-1 * FFT_{omega^-1}(g), affine in, affine out */
 int zkgpu_g_to_lagrange(const uint64_t* g_affine, uint32_t k, uint64_t* out_affine);
 
+/* ParamsKZG::setup(k, SmallRng::seed_from_u64(seed)) — the seeded SRS of the reference's prove/verify tests
+ * (/root/reference/crates/halo2-verifier/src/generator.rs:118-119): g[i] = G * s^i, g_lagrange = g_to_lagrange(g). */
+int zkgpu_params_setup(uint32_t k, uint64_t seed, uint64_t* g_out, uint64_t* g_lagrange_out);
+
+/* ---- vectorised Fr helpers (halo2curves `Fr` ops / `Fr::random`), used to build synthetic circuits and
+ * witnesses in bench.py without the CPU oracle.  op: 0 mul, 1 add, 2 sub, 3 to Montgomery, 4 from Montgomery. */
+int zkgpu_fr_vec_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+int zkgpu_fr_to_mont(const uint64_t* canonical, uint64_t* out, size_t n);
+int zkgpu_fr_from_mont(const uint64_t* mont, uint64_t* out, size_t n);
+int zkgpu_fr_random(uint64_t seed, uint64_t* out, size_t n);
+
 /* ---- device-resident variants (inputs already in HBM; `stream` is a cudaStream_t or NULL) ------
  * Used by the prover pipeline and by bench.py's kernel-only ("value") measurement. */
 int zkgpu_ntt_fr_batch_dev(void* d_a, const uint64_t omega[4], uint32_t log_n, size_t m, void* d_scratch, void* stream);
 int zkgpu_msm_g1_srs_batch_dev(uint64_t srs, int basis, const void* d_scalars, size_t n, size_t m, void* d_out_affine, void* stream);
+/* ---- batched prover: halo2_proofs::plonk::{keygen_vk, keygen_pk, create_proof} -------------------
+ * The funnel every Shielder prover host goes through is
+ *   shielder_circuits::generate_proof(&params, &pk, circuit, &public_input, rng) -> Vec<u8>
+ * (/root/reference/crates/shielder_bindings/src/circuits/mod.rs:103-111,
+ *  /root/reference/crates/shielder-account/src/call_data.rs:489-501,
+ *  /root/reference/tee/crates/shielder-prover-tee/src/circuits/mod.rs:70-78), one circuit + one instance
+ * column per proof, Keccak256 EVM transcript, SHPLONK.  zkgpu_prove_batch runs m such proofs of the same
+ * circuit in lock step on the GPU.
+ *
+ * zkgpu_pk_create = generate_keys_with_min_k's keygen_vk + keygen_pk for a fixed k
+ * (/root/reference/crates/shielder_bindings/build.rs:22): `circuit_blob` is the serialised constraint
+ * system + fixed assignment + copy constraints (layout: zkgpu/circuits.py Circuit._serialize), i.e. what
+ * halo2's `ConstraintSystem` and keygen `Assembly` hold after `Circuit::configure` / `synthesize`.
+ * The SRS handle must have been registered with the same k (ParamsKZG::downsize first). */
+int zkgpu_pk_create(uint64_t srs, const uint8_t* circuit_blob, size_t blob_len, uint64_t* pk_out);
+int zkgpu_pk_release(uint64_t pk);
+/* info[0..13] = k, n, num_advice, num_fixed, degree, blinding_factors, num_perm_sets, num_quotients,
+ *               num_evals, proof_len, extended_k, num_perm_columns, num_rotation_sets, sub_batch */
+int zkgpu_pk_info(uint64_t pk, uint64_t info[16]);
+/* VerifyingKey parts: fixed commitments (F x 8 u64 affine), permutation commitments (S x 8), transcript_repr (4) */
+int zkgpu_pk_vk(uint64_t pk, uint64_t* fixed_commitments, uint64_t* perm_commitments, uint64_t digest[4]);
+/* m proofs.  advice: m x num_advice x n field elements — the assigned advice columns `create_proof` holds
+ * after witness synthesis (rows >= n - (blinding_factors + 1) are overwritten with blinding values);
+ * instance: m x num_instance public inputs; rng_seeds[i] seeds proof i's `SmallRng::seed_from_u64`
+ * (/root/reference/crates/shielder-setup/lib.rs:29-40); proofs_out: m x proof_len bytes, each exactly what
+ * `transcript.finalize()` returns (/root/reference/crates/halo2-verifier/src/lib/verifier_contract.rs:14-20). */
+int zkgpu_prove_batch(uint64_t pk, const uint64_t* advice, const uint64_t* instance, size_t num_instance, size_t m,
+                      const uint64_t* rng_seeds, uint8_t* proofs_out, size_t proof_len);
+/* same with the advice columns already resident in HBM */
+int zkgpu_prove_batch_dev(uint64_t pk, const void* d_advice, const uint64_t* instance, size_t num_instance, size_t m,
+                          const uint64_t* rng_seeds, uint8_t* proofs_out, size_t proof_len);
+/* profiling aid: accumulated wall-clock seconds per prover step (0 upload, 1 advice commit, 2 permutation +
+ * random poly, 3 quotient, 4 evaluations, 5 SHPLONK h, 6 SHPLONK L); reset != 0 zeroes the counters */
+void zkgpu_prover_step_seconds(double out[8], int reset);
+/* test hook: called with (stage name, field elements of proof 0 of each sub-batch, byte count) */
+void zkgpu_set_trace(void (*fn)(const char* name, const void* data, size_t bytes));
+
 /* number of kernel launches issued by this library in this process so far */
 uint64_t zkgpu_launch_count(void);
 

@@ -12,6 +12,7 @@
 #pragma once
 #include "bn254.hpp"
 #include "misc.hpp"
+#include "arith.hpp"
 #include "final_exp.inc"
 
 namespace oracle {
@@ -128,6 +129,68 @@ static inline Fq12 final_exponentiation(const Fq12& f) {
         for (int b = 3; b >= 0; --b) { acc = acc.square(); if ((d >> b) & 1) acc = acc * g; }
     }
     return acc;
+}
+
+// k * Q on the twist (affine double-and-add; used once per synthetic SRS for s_g2 = s * g2)
+static inline G2AffineRaw g2_mul(const G2AffineRaw& q, const Fr& k) {
+    U256 e = k.to_u256();
+    bool inf = true;
+    Fq2 rx = Fq2::zero(), ry = Fq2::zero();
+    const Fq2 qx{q.x0, q.x1}, qy{q.y0, q.y1};
+    const Fq2 three{Fq::from_u64(3), Fq::zero()};
+    for (int i = 255; i >= 0; --i) {
+        if (!inf) {
+            if (ry.is_zero()) inf = true;
+            else {
+                Fq2 lam = (rx.square() * three) * (ry + ry).inv();
+                Fq2 nx = lam.square() - rx - rx;
+                ry = lam * (rx - nx) - ry; rx = nx;
+            }
+        }
+        if ((e.l[i / 64] >> (i % 64)) & 1) {
+            if (inf) { rx = qx; ry = qy; inf = false; }
+            else if (rx == qx) {
+                if (ry == qy) { Fq2 lam = (rx.square() * three) * (ry + ry).inv(); Fq2 nx = lam.square() - rx - rx; ry = lam * (rx - nx) - ry; rx = nx; }
+                else inf = true;
+            } else {
+                Fq2 lam = (qy - ry) * (qx - rx).inv();
+                Fq2 nx = lam.square() - rx - qx;
+                ry = lam * (rx - nx) - ry; rx = nx;
+            }
+        }
+    }
+    if (inf) return {Fq::zero(), Fq::zero(), Fq::zero(), Fq::zero()};
+    return {rx.c0, rx.c1, ry.c0, ry.c1};
+}
+
+// `ParamsKZG::setup(k, rng)` (halo2_proofs poly/kzg/commitment.rs [UPSTREAM-MEMORY, SURVEY Appendix A]), the
+// SRS the reference's seeded tests build (/root/reference/crates/halo2-verifier/src/generator.rs:118-119):
+// s = Fr::random(rng); g[i] = G * s^i; g_lagrange[i] = G * ((s^n - 1)/n * w^i / (s - w^i)); s_g2 = s * g2.
+static inline Srs params_setup(unsigned k, RngCore& rng, const G2AffineRaw& g2_generator, unsigned threads) {
+    Srs out; out.k = k;
+    const size_t n = (size_t)1 << k;
+    Fr s = random_field<Fr>(rng);
+    EvaluationDomain d(2, k);
+    std::vector<G1> gp(n), glp(n);
+    const G1 G = G1::from_affine(G1Affine::generator());
+    Fr sn_m1_over_n = (s.pow_u64(n) - Fr::one()) * Fr::from_u64(n).inv();
+    std::vector<Fr> den(n);
+    { Fr w = Fr::one(); for (size_t i = 0; i < n; ++i) { den[i] = s - w; w = w * d.omega; } }
+    batch_invert(den.data(), n);
+    parallel_chunks(n, threads, [&](size_t a, size_t b) {
+        Fr sp = s.pow_u64(a), w = d.omega.pow_u64(a);
+        for (size_t i = a; i < b; ++i) {
+            gp[i] = G.mul(sp);
+            glp[i] = G.mul(sn_m1_over_n * w * den[i]);
+            sp = sp * s; w = w * d.omega;
+        }
+    });
+    out.g.resize(n); out.g_lagrange.resize(n);
+    batch_normalize(gp.data(), out.g.data(), n);
+    batch_normalize(glp.data(), out.g_lagrange.data(), n);
+    out.g2 = g2_generator;
+    out.s_g2 = g2_mul(g2_generator, s);
+    return out;
 }
 
 // e(p1,q1) * e(p2,q2) == 1 ?

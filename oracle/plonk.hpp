@@ -381,7 +381,11 @@ static inline std::vector<Fr> lagrange_interpolate(const std::vector<Fr>& pts, c
 // ---------------------------------------------------------------------------------------------
 // create_proof
 // ---------------------------------------------------------------------------------------------
-struct ProverStats { size_t msms = 0, ntts = 0, ext_ntts = 0; };
+struct ProverStats {
+    size_t msms = 0, ntts = 0, ext_ntts = 0;
+    // optional stage trace (tests): called with a stage name and the stage's field elements
+    std::function<void(const char*, const Fr*, size_t)> trace;
+};
 
 static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const ProvingKey& pk,
                                                 std::vector<std::vector<Fr>> advice,  // num_advice x n, assigned cells
@@ -392,6 +396,9 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
     const unsigned bf = cs.blinding_factors();
     const size_t unusable_start = n - (bf + 1);
     ProverStats st;
+    if (stats) st.trace = stats->trace;
+    auto trace = [&](const char* name, const std::vector<Fr>& v) { if (st.trace) st.trace(name, v.data(), v.size()); };
+    auto trace2 = [&](const char* name, const std::vector<std::vector<Fr>>& vv) { if (st.trace) for (auto& v : vv) st.trace(name, v.data(), v.size()); };
     if (advice.size() != cs.num_advice) throw std::runtime_error("create_proof: wrong number of advice columns");
     for (auto& col : advice) if (col.size() != n) throw std::runtime_error("create_proof: advice column length != n");
     if (instance.size() > unusable_start) throw std::runtime_error("create_proof: InstanceTooLarge");
@@ -406,6 +413,7 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
     // advice: blind the unusable rows (column-major), one unused Blind per column, commit
     for (auto& col : advice) for (size_t i = unusable_start; i < n; ++i) col[i] = random_field<Fr>(rng);
     for (size_t i = 0; i < advice.size(); ++i) (void)random_field<Fr>(rng);
+    trace2("advice_blinded", advice);
     for (auto& col : advice) { tr.write_point(params.commit_lagrange(col)); st.msms++; }
 
     Fr theta = tr.squeeze_challenge(); (void)theta;
@@ -439,6 +447,7 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
             for (size_t i = n - bf; i < n; ++i) z[i] = random_field<Fr>(rng);
             last_z = z[n - (bf + 1)];
             (void)random_field<Fr>(rng);  // Blind
+            trace("z", z);
             tr.write_point(params.commit_lagrange(z)); st.msms++;
             std::vector<Fr> zc = d.lagrange_to_coeff(z); st.ntts++;
             z_cosets.push_back(d.coeff_to_extended(zc)); st.ext_ntts++;
@@ -453,6 +462,7 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
         ChaCha20Rng crng(seed);
         for (auto& v : random_poly) v = random_field<Fr>(crng);
         (void)random_field<Fr>(rng);  // Blind
+        trace("random_poly", random_poly);
         tr.write_point(params.commit(random_poly)); st.msms++;
     }
 
@@ -461,12 +471,17 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
     std::vector<std::vector<Fr>> advice_polys;
     for (auto& col : advice) { advice_polys.push_back(d.lagrange_to_coeff(col)); st.ntts++; }
 
+    trace2("advice_poly", advice_polys);
+    trace2("z_poly", z_polys);
+    trace2("z_coset", z_cosets);
     // evaluate_h on the extended coset
     std::vector<Fr> h(en, Fr::zero());
     {
         std::vector<std::vector<Fr>> advice_cosets, instance_cosets;
         for (auto& p : advice_polys) { advice_cosets.push_back(d.coeff_to_extended(p)); st.ext_ntts++; }
         instance_cosets.push_back(d.coeff_to_extended(instance_poly)); st.ext_ntts++;
+        trace2("advice_coset", advice_cosets);
+        trace2("instance_coset", instance_cosets);
         const long rot_scale = (long)1 << (d.extended_k - d.k);
         auto ridx = [&](size_t i, int r) { return (size_t)((((long)i + r * rot_scale) % (long)en + (long)en) % (long)en); };
         auto col_coset = [&](const ColumnRef& c) -> const std::vector<Fr>& {
@@ -511,7 +526,9 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
 
     // vanishing construct: divide by X^n - 1 on the coset, back to coefficients, split, commit pieces
     d.divide_by_vanishing_poly(h);
+    trace("h_evals", h);
     std::vector<Fr> h_coeffs = d.extended_to_coeff(h); st.ext_ntts++;
+    trace("h_coeffs", h_coeffs);
     const unsigned Q = cs.num_quotients();
     std::vector<std::vector<Fr>> h_pieces;
     for (unsigned i = 0; i < Q; ++i) h_pieces.emplace_back(h_coeffs.begin() + i * n, h_coeffs.begin() + (i + 1) * n);
@@ -534,6 +551,8 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
         evals.push_back(eval_polynomial(z_polys[s].data(), n, d.rotate_omega(x, 1)));
         if (s + 1 < z_polys.size()) evals.push_back(eval_polynomial(z_polys[s].data(), n, d.rotate_omega(x, cs.rotation_last())));
     }
+    trace("evals", evals);
+    trace("h_poly", h_poly);
     for (auto& e : evals) tr.write_scalar(e);
     evals.push_back(eval_polynomial(h_poly.data(), n, x));  // "computed" quotient eval: not written
 
@@ -574,6 +593,8 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
             set_combined.push_back(std::move(comb)); set_r.push_back(std::move(rcomb));
         }
     }
+    trace2("set_combined", set_combined);
+    trace("hx", hx);
     tr.write_point(params.commit(hx)); st.msms++;
     Fr mu = tr.squeeze_challenge();
     {
@@ -593,9 +614,11 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
         for (size_t t = 0; t < n; ++t) lx[t] = (lx[t] - hx[t] * z_t) * zdiff0_inv;
         std::vector<Fr> wq = kate_division(lx, mu);
         wq.resize(n, Fr::zero());
+        trace("lx", lx);
+        trace("wq", wq);
         tr.write_point(params.commit(wq)); st.msms++;
     }
-    if (stats) *stats = st;
+    if (stats) { stats->msms = st.msms; stats->ntts = st.ntts; stats->ext_ntts = st.ext_ntts; }
     if (tr.proof.size() != cs.proof_len()) throw std::runtime_error("create_proof: proof length mismatch");
     return tr.proof;
 }

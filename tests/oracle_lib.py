@@ -179,6 +179,21 @@ def g2_on_curve(q):
     return bool(lib().orc_g2_on_curve(_p(q)))
 
 
+TRACE_FN = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p, C.c_size_t)
+
+
+def params_setup(k, seed, threads=8):
+    """ParamsKZG::setup(k, SmallRng::seed_from_u64(seed)) as the reference's seeded tests do
+    (crates/halo2-verifier/src/generator.rs:118-119).  G2 generator from the ppot fixture."""
+    n = 1 << k
+    gen = srs_read(RAW11, 0)["g2"]
+    g = np.empty((n, 8), dtype=np.uint64)
+    gl = np.empty((n, 8), dtype=np.uint64)
+    g2s = np.empty((2, 16), dtype=np.uint64)
+    _chk(lib().orc_params_setup(k, C.c_uint64(seed), _p(np.ascontiguousarray(gen)), threads, _p(g), _p(gl), _p(g2s)))
+    return dict(k=k, g=g, g_lagrange=gl, g2=g2s[0].copy(), s_g2=g2s[1].copy())
+
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 RAW11 = os.path.join(GOLDEN, "ppot_0080_11_raw.bin")
 

@@ -46,3 +46,4 @@ def test_limb_arithmetic_matches_oracle(emu, field, p):
     for op, oop in ((0, 0), (1, 1), (2, 2)):
         assert np.array_equal(run(emu, field, op, a, b), O.field_op(field, oop, a, b).reshape(-1, 4)), op
     assert np.array_equal(run(emu, field, 3, a), O.field_op(field, 4, a).reshape(-1, 4))
+

@@ -4,8 +4,11 @@
 // CUDA is unavailable every compute call returns ZKGPU_ERR_CUDA.
 #include "../../include/zkgpu.h"
 #include "context.cuh"
+#include "prover_kernels.cuh"
+#include "host_util.hpp"
 
 namespace zk {
+void prover_release_all();  // prover.cu
 std::atomic<uint64_t> g_launches{0};
 Context& ctx() { static Context c; return c; }
 thread_local std::string g_last_error;
@@ -38,6 +41,7 @@ void Context::shutdown() {
     std::lock_guard<std::recursive_mutex> lk(mu);
     if (!inited) return;
     cudaStreamSynchronize(stream);
+    prover_release_all();
     srs.clear();
     ws = MsmWorkspace();
     fr_buf.release(); fr_scratch.release(); pt_buf.release(); xyzz_buf.release(); aff_buf.release();
@@ -89,7 +93,7 @@ using namespace zk;
 
 extern "C" {
 
-int zkgpu_abi_version(void) { return 1; }
+int zkgpu_abi_version(void) { return 2; }
 const char* zkgpu_last_error(void) { return g_last_error.c_str(); }
 uint64_t zkgpu_launch_count(void) { return g_launches.load(); }
 
@@ -276,6 +280,42 @@ int zkgpu_coset_intt_fr(uint64_t* evals, uint32_t k, uint32_t ext_k, uint32_t qu
     ZK_CUDA(cudaMemcpyAsync(evals, C.fr_buf.p, keep * 32, cudaMemcpyDeviceToHost, st));
     ZK_CUDA(cudaStreamSynchronize(st));
     memset(evals + 4 * keep, 0, (en - keep) * 32);
+    API_END
+}
+
+/* ---- vectorised Fr helpers (synthetic circuit / witness construction in bench.py and tools) ------ */
+int zkgpu_fr_vec_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    API_BEGIN
+    Context& C = ctx(); C.require();
+    ZK_REQUIRE(op >= 0 && op <= 4 && a && out && (b || op >= 3), "fr_vec_op: bad arguments");
+    if (n == 0) return ZKGPU_OK;
+    cudaStream_t st = C.stream;
+    C.fr_buf.ensure(3 * n);
+    ZK_CUDA(cudaMemcpyAsync(C.fr_buf.p, a, n * 32, cudaMemcpyHostToDevice, st));
+    if (op < 3) ZK_CUDA(cudaMemcpyAsync(C.fr_buf.p + n, b, n * 32, cudaMemcpyHostToDevice, st));
+    launch_vec_op(op, C.fr_buf.p, C.fr_buf.p + n, C.fr_buf.p + 2 * n, n, st);
+    ZK_CUDA(cudaMemcpyAsync(out, C.fr_buf.p + 2 * n, n * 32, cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(cudaStreamSynchronize(st));
+    API_END
+}
+int zkgpu_fr_to_mont(const uint64_t* canonical, uint64_t* out, size_t n) { return zkgpu_fr_vec_op(3, canonical, nullptr, out, n); }
+int zkgpu_fr_from_mont(const uint64_t* mont, uint64_t* out, size_t n) { return zkgpu_fr_vec_op(4, mont, nullptr, out, n); }
+/* out[i] = Fr::random(rng) for rng = SmallRng::seed_from_u64(seed) (eight next_u64 each, 512-bit reduction) */
+int zkgpu_fr_random(uint64_t seed, uint64_t* out, size_t n) {
+    API_BEGIN
+    Context& C = ctx(); C.require();
+    ZK_REQUIRE(out || n == 0, "null pointer");
+    if (n == 0) return ZKGPU_OK;
+    cudaStream_t st = C.stream;
+    std::vector<uint64_t> raw(8 * n);
+    SmallRng rng(seed);
+    for (size_t i = 0; i < 8 * n; ++i) raw[i] = rng.next_u64();
+    C.fr_buf.ensure(3 * n);
+    uint64_t* d_raw = reinterpret_cast<uint64_t*>(C.fr_buf.p + n);
+    ZK_CUDA(cudaMemcpyAsync(d_raw, raw.data(), raw.size() * 8, cudaMemcpyHostToDevice, st));
+    launch_reduce_wide(d_raw, C.fr_buf.p, n, st);
+    ZK_CUDA(cudaMemcpyAsync(out, C.fr_buf.p, n * 32, cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(cudaStreamSynchronize(st));
     API_END
 }
 

@@ -75,6 +75,26 @@ __host__ __device__ __forceinline__ Fe<Tag> from_mont(const Fe<Tag>& a) {
 template <class Tag>
 __host__ __device__ __forceinline__ Fe<Tag> to_mont(const Fe<Tag>& a) { return a * fe_r2<Tag>(); }
 
+// Any 256-bit integer -> the same value mod r.  The Montgomery limb code needs operands < p (its dropped
+// carries are provably zero only then — asserted by the host emulation in tests/test_fp_emulation.py),
+// so raw RNG / hash words pass through here first.  2^256 < 6r: at most five subtractions.
+__host__ __device__ __forceinline__ void fr_reduce_raw(fr_t& v) {
+    const uint32_t M[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    for (int it = 0; it < 5; ++it) {
+        uint32_t t[8];
+        uint32_t borrow = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint64_t d = (uint64_t)v.l[i] - M[i] - borrow;
+            t[i] = (uint32_t)d;
+            borrow = (uint32_t)(d >> 63);
+        }
+        if (borrow) break;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v.l[i] = t[i];
+    }
+}
+
 // a^e for a 256-bit exponent given as 8 u32 limbs (LE); used for inversion (e = p-2)
 template <class Tag>
 __host__ __device__ inline Fe<Tag> fe_pow(const Fe<Tag>& a, const uint32_t* e) {

@@ -39,13 +39,14 @@ __host__ __device__ __forceinline__ void for_each_digit(const uint32_t* s, unsig
     }
 }
 
-struct MsmDims { unsigned c, W, G, nb; unsigned precomp; unsigned n; unsigned tstride; };  // tstride: table stride (points per window)
+struct MsmDims { unsigned c, W, G, nb; unsigned precomp; unsigned n; unsigned tstride; size_t inner, outer_stride; };  // tstride: table stride (points per window)
 
 __global__ void k_msm_count(const fr_t* __restrict__ scalars, size_t total, MsmDims D, uint32_t* __restrict__ counts) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     size_t m = idx / D.n;
-    fr_t s = from_mont(fe_load(scalars + idx));
+    size_t i_ = idx - m * D.n;
+    fr_t s = from_mont(fe_load(scalars + (m / D.inner) * D.outer_stride + (m % D.inner) * D.n + i_));
     uint32_t* cm = counts + m * ((size_t)D.G * D.nb);
     for_each_digit(s.l, D.c, D.W, [&](unsigned w, uint32_t mag, bool) {
         unsigned g = D.precomp ? 0 : w;
@@ -82,7 +83,7 @@ __global__ void k_msm_scatter(const fr_t* __restrict__ scalars, size_t total, Ms
     if (idx >= total) return;
     size_t m = idx / D.n;
     uint32_t i = (uint32_t)(idx - m * D.n);
-    fr_t s = from_mont(fe_load(scalars + idx));
+    fr_t s = from_mont(fe_load(scalars + (m / D.inner) * D.outer_stride + (m % D.inner) * D.n + i));
     const size_t K = (size_t)D.G * D.nb;
     uint32_t* cm = counts + m * K;
     const uint32_t* om = offsets + m * (K + 1);
@@ -222,6 +223,7 @@ void MsmWorkspace::ensure(const MsmPlan& p, size_t M) {
 
 static MsmDims dims_of(const MsmPlan& p) {
     MsmDims D; D.c = p.c; D.W = p.W; D.G = p.G; D.nb = p.nb; D.precomp = p.precomp ? 1 : 0; D.n = (unsigned)p.n; D.tstride = (unsigned)(p.tstride ? p.tstride : p.n);
+    D.inner = p.inner ? p.inner : ~(size_t)0; D.outer_stride = p.outer_stride;
     return D;
 }
 

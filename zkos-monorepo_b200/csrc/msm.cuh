@@ -14,6 +14,8 @@ struct MsmPlan {
     bool precomp = false;
     size_t n = 0;        // scalars per MSM
     size_t tstride = 0;  // precomp: points per window in the table (0 = n)
+    // optional two-level scalar addressing: MSM m reads scalars at (m / inner) * outer_stride + (m % inner) * n
+    size_t inner = 0, outer_stride = 0;
     size_t K() const { return (size_t)G * nb; }            // buckets per MSM
     size_t entries_per_msm() const { return n * W; }
 };

@@ -29,6 +29,7 @@ struct NttPass {
     unsigned log_N, log_m, log_C, swz_q;
     unsigned tiles_per_poly;
     size_t in_poly_stride, out_poly_stride;
+    size_t in_inner, in_outer_stride, out_inner, out_outer_stride;  // poly p -> (p / inner) * outer_stride + (p % inner) * poly_stride
     size_t in_tile_stride, in_sj, in_sc;
     size_t out_tile_stride, out_sj, out_sc;
     size_t in_valid;     // elements >= in_valid (index within the polynomial) read as zero
@@ -64,8 +65,8 @@ __global__ void __launch_bounds__(1024, 1) k_ntt_tile(const NttPass P) {
     const unsigned m = 1u << log_m, C = 1u << log_C, total = m << log_C;
     const unsigned tile = blockIdx.x % P.tiles_per_poly;
     const size_t poly = blockIdx.x / P.tiles_per_poly;
-    const fr_t* in = P.in + poly * P.in_poly_stride + (size_t)tile * P.in_tile_stride;
-    fr_t* out = P.out + poly * P.out_poly_stride + (size_t)tile * P.out_tile_stride;
+    const fr_t* in = P.in + (poly / P.in_inner) * P.in_outer_stride + (poly % P.in_inner) * P.in_poly_stride + (size_t)tile * P.in_tile_stride;
+    fr_t* out = P.out + (poly / P.out_inner) * P.out_outer_stride + (poly % P.out_inner) * P.out_poly_stride + (size_t)tile * P.out_tile_stride;
 
     for (unsigned e = threadIdx.x; e < total; e += blockDim.x) {
         unsigned c, j;
@@ -236,6 +237,8 @@ void ntt_run(const NttJob& J, cudaStream_t st) {
     P.tw = tw; P.log_N = log_N;
     P.in_poly_stride = J.in_stride ? J.in_stride : N;
     P.out_poly_stride = J.out_stride ? J.out_stride : N;
+    P.in_inner = J.in_inner ? J.in_inner : ~(size_t)0; P.in_outer_stride = J.in_outer_stride;
+    P.out_inner = J.out_inner ? J.out_inner : ~(size_t)0; P.out_outer_stride = J.out_outer_stride;
     P.in_valid = J.in_valid ? J.in_valid : N;
     fr_t one = fe_one<FrTag>();
     P.cs1 = J.pre_coset ? J.cs1 : (J.post_coset ? J.cs1 : one);
@@ -261,7 +264,7 @@ void ntt_run(const NttJob& J, cudaStream_t st) {
     {
         NttPass A = P;
         A.in = J.in; A.out = J.scratch;
-        A.out_poly_stride = N;
+        A.out_poly_stride = N; A.out_inner = ~(size_t)0; A.out_outer_stride = 0;
         A.log_m = log_n1; A.log_C = pick_c(log_n1); A.swz_q = pick_swz(A.log_m, A.log_C);
         unsigned C = 1u << A.log_C;
         A.tiles_per_poly = (unsigned)(n2 >> A.log_C);
@@ -276,7 +279,7 @@ void ntt_run(const NttJob& J, cudaStream_t st) {
     {
         NttPass B = P;
         B.in = J.scratch; B.out = J.out;
-        B.in_poly_stride = N; B.in_valid = N;
+        B.in_poly_stride = N; B.in_valid = N; B.in_inner = ~(size_t)0; B.in_outer_stride = 0;
         B.log_m = log_n2; B.log_C = pick_c(log_n2); B.swz_q = pick_swz(B.log_m, B.log_C);
         unsigned C = 1u << B.log_C;
         B.tiles_per_poly = (unsigned)(n1 >> B.log_C);

@@ -15,6 +15,8 @@ struct NttJob {
     size_t batch = 1;
     unsigned log_n = 0;
     size_t in_stride = 0, out_stride = 0;
+    // optional two-level batch addressing: polynomial p lives at (p / inner) * outer_stride + (p % inner) * stride
+    size_t in_inner = 0, in_outer_stride = 0, out_inner = 0, out_outer_stride = 0;
     size_t in_valid = 0;        // 0 = N; inputs at index >= in_valid read as zero (zero-padding)
     fr_t omega;
     int pre_coset = 0, post_coset = 0;  // multiply element i by cs1 / cs2 when i%3 == 1 / 2

@@ -1,0 +1,66 @@
+// `ParamsKZG::setup(k, rng)` on the device — the seeded test SRS the reference's own prove/verify tests build
+// (/root/reference/crates/halo2-verifier/src/generator.rs:118-119, rng = SmallRng::seed_from_u64(42),
+// /root/reference/crates/shielder-setup/lib.rs:29-40): s = Fr::random(rng), g[i] = G * s^i,
+// g_lagrange = g_to_lagrange(g) (K6, g1fft.cu).  The production SRS comes from the ppot ceremony files
+// through crates/powers-of-tau instead; k = 13 of that ceremony is not in the reference tree
+// (.MISSING_LARGE_BLOBS), which is why the benchmark uses this setup.
+#include "../../include/zkgpu.h"
+#include "context.cuh"
+#include "host_util.hpp"
+
+namespace zk {
+
+__global__ void __launch_bounds__(64) k_fixed_base_mul(const fr_t* __restrict__ scalars, g1_affine_t base, g1_xyzz_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_t s = from_mont(fe_load(scalars + i));
+    g1_xyzz_t r = xyzz_mul(g1_xyzz_t::from_affine(base), s.l);
+    fe_store(&out[i].x, r.x); fe_store(&out[i].y, r.y); fe_store(&out[i].zz, r.zz); fe_store(&out[i].zzz, r.zzz);
+}
+
+}  // namespace zk
+
+using namespace zk;
+
+extern "C" int zkgpu_params_setup(uint32_t k, uint64_t seed, uint64_t* g_out, uint64_t* g_lagrange_out) {
+    try {
+        std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+        Context& C = ctx(); C.require();
+        ZK_REQUIRE(g_out && g_lagrange_out, "null pointer");
+        ZK_REQUIRE(k >= 1 && k <= 20, "params_setup: k out of range");
+        const size_t n = (size_t)1 << k;
+        cudaStream_t st = C.stream;
+        // s = Fr::random(rng) = from_u512 of eight next_u64
+        SmallRng rng(seed);
+        uint64_t w[8]; rng.next_wide(w);
+        fr_t lo, hi;
+        for (int i = 0; i < 4; ++i) {
+            lo.l[2 * i] = (uint32_t)w[i]; lo.l[2 * i + 1] = (uint32_t)(w[i] >> 32);
+            hi.l[2 * i] = (uint32_t)w[4 + i]; hi.l[2 * i + 1] = (uint32_t)(w[4 + i] >> 32);
+        }
+        fr_reduce_raw(lo); fr_reduce_raw(hi);
+        fr_t r2 = fe_r2<FrTag>();
+        fr_t s = lo * r2 + hi * (r2 * r2);
+        std::vector<fr_t> pows(n);
+        fr_t cur = fe_one<FrTag>();
+        for (size_t i = 0; i < n; ++i) { pows[i] = cur; cur = cur * s; }
+        g1_affine_t G;
+        G.x = fq_t::zero(); G.y = fq_t::zero();
+        G.x.l[0] = 1; G.y.l[0] = 2;
+        G.x = to_mont(G.x); G.y = to_mont(G.y);
+        C.fr_buf.ensure(n); C.xyzz_buf.ensure(n); C.aff_buf.ensure(n); C.pt_buf.ensure(n);
+        ZK_CUDA(cudaMemcpyAsync(C.fr_buf.p, pows.data(), n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+        ZK_LAUNCH(k_fixed_base_mul, ceil_div(n, 64), 64, 0, st, C.fr_buf.p, G, C.xyzz_buf.p, n);
+        g1_normalize(C.xyzz_buf.p, C.pt_buf.p, n, st);
+        ZK_CUDA(cudaMemcpyAsync(g_out, C.pt_buf.p, n * 64, cudaMemcpyDeviceToHost, st));
+        // g_lagrange = n^-1 * FFT_{omega^-1}(g)
+        g1_from_affine(C.pt_buf.p, C.xyzz_buf.p, n, st);
+        g1_fft(C.xyzz_buf.p, k, fr_omega_inv(k), st);
+        g1_scale(C.xyzz_buf.p, n, fr_pow2_inv(k), st);
+        g1_normalize(C.xyzz_buf.p, C.aff_buf.p, n, st);
+        ZK_CUDA(cudaMemcpyAsync(g_lagrange_out, C.aff_buf.p, n * 64, cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(cudaStreamSynchronize(st));
+        return ZKGPU_OK;
+    } catch (const zk::Error& e) { g_last_error = e.what(); return e.code; }
+    catch (const std::exception& e) { g_last_error = e.what(); return ZKGPU_ERR_INTERNAL; }
+}

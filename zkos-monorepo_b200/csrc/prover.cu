@@ -1,0 +1,855 @@
+// Batched halo2 `create_proof` on the device — the C++ host driver of the proving pipeline.
+//
+// Replaces, for a batch of independent proofs of ONE circuit, what Shielder reaches through
+//   shielder_circuits::generate_proof(&params, &pk, circuit, &public_input, rng)
+//     -> halo2_proofs::plonk::create_proof::<KZGCommitmentScheme<Bn256>, ProverSHPLONK, ChallengeEvm, _,
+//        Keccak256Transcript, _>
+// (/root/reference/crates/shielder_bindings/src/circuits/mod.rs:103-111,
+//  /root/reference/tee/crates/shielder-prover-tee/src/circuits/mod.rs:70-78).  Step order, RNG draw
+// order and transcript writes follow halo2 v0.3.0 plonk/prover.rs, permutation/prover.rs,
+// vanishing/prover.rs and poly/kzg/multiopen/shplonk/prover.rs; the proof
+// layout is the one the in-repo verifier generator reads
+// (/root/reference/crates/halo2-verifier/src/lib/codegen/util.rs:226-245,
+//  /root/reference/crates/halo2-verifier/templates/Halo2Verifier.sol:247-307).
+//
+// Everything that scales with n runs on the GPU (MSM, NTT, grand products, quotient evaluation,
+// Horner evaluations, SHPLONK polynomial algebra); the host keeps only the Fiat-Shamir transcript
+// (Keccak), the seeded RNG stream and O(#queries) scalar bookkeeping per proof.  A sub-batch of B
+// proofs advances in lock step so every kernel launch covers B proofs; the six transcript round trips
+// (theta/beta/gamma, y, x, zeta/nu, mu) are the only host synchronisation points.
+// Witness synthesis (the circuit's own Rust code) is outside the path: the caller passes assigned
+// advice columns, as `create_proof` has them after `synthesize`.
+#include "../../include/zkgpu.h"
+#include "context.cuh"
+#include "prover_kernels.cuh"
+#include "plonk_types.hpp"
+#include "host_util.hpp"
+#include <map>
+#include <set>
+#include <cstdlib>
+#include <chrono>
+
+namespace zk {
+
+typedef void (*trace_fn)(const char* name, const void* data, size_t bytes);
+static trace_fn g_trace = nullptr;
+// wall-clock seconds spent in each step of prove_sub_batch (every step ends in a stream sync)
+static double g_step_s[8] = {0};
+struct StepTimer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(int step) {
+        auto t1 = std::chrono::steady_clock::now();
+        g_step_s[step] += std::chrono::duration<double>(t1 - t0).count();
+        t0 = t1;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// SHPLONK query plan: queries in the order of codegen/pcs.rs:60-104, rotation sets as
+// pcs/bdfg21.rs:443-494 builds them (first-seen order of distinct rotation sets).
+// commitment ids: [0,A) advice | P perm z | F fixed | S sigma | h | random
+// ---------------------------------------------------------------------------------------------
+struct RotSet {
+    std::vector<int> rots, diffs, comms;
+    std::vector<std::vector<int>> evals;  // [comm][rot] -> index into the eval list
+};
+struct QueryPlan {
+    std::vector<int> superset;
+    std::vector<RotSet> sets;
+    int id_z0 = 0, id_fixed0 = 0, id_sigma0 = 0, id_h = 0, id_random = 0;
+    void build(const CsDesc& cs) {
+        const int A = cs.num_advice, P = cs.num_perm_sets(), F = cs.num_fixed, S = (int)cs.perm_columns.size();
+        id_z0 = A; id_fixed0 = A + P; id_sigma0 = A + P + F; id_h = A + P + F + S; id_random = id_h + 1;
+        const int e_fix = (int)cs.advice_queries.size(), e_rand = e_fix + (int)cs.fixed_queries.size();
+        const int e_sigma = e_rand + 1, e_z = e_sigma + S, e_h = (int)cs.num_evals();
+        struct Q { int comm, rot, eval; };
+        std::vector<Q> qs;
+        for (size_t i = 0; i < cs.advice_queries.size(); ++i) qs.push_back({(int)cs.advice_queries[i].column, cs.advice_queries[i].rotation, (int)i});
+        for (int s = 0; s < P; ++s) { qs.push_back({id_z0 + s, 0, e_z + 3 * s}); qs.push_back({id_z0 + s, 1, e_z + 3 * s + 1}); }
+        for (int s = P - 2; s >= 0; --s) qs.push_back({id_z0 + s, cs.rotation_last(), e_z + 3 * s + 2});
+        for (size_t i = 0; i < cs.fixed_queries.size(); ++i) qs.push_back({id_fixed0 + (int)cs.fixed_queries[i].column, cs.fixed_queries[i].rotation, e_fix + (int)i});
+        for (int s = 0; s < S; ++s) qs.push_back({id_sigma0 + s, 0, e_sigma + s});
+        qs.push_back({id_h, 0, e_h});
+        qs.push_back({id_random, 0, e_rand});
+        std::set<int> sup;
+        std::vector<std::pair<int, std::map<int, int>>> per_comm;  // first-seen order of commitments
+        for (auto& q : qs) {
+            sup.insert(q.rot);
+            size_t j = 0;
+            while (j < per_comm.size() && per_comm[j].first != q.comm) ++j;
+            if (j == per_comm.size()) per_comm.push_back({q.comm, {}});
+            per_comm[j].second[q.rot] = q.eval;
+        }
+        superset.assign(sup.begin(), sup.end());
+        for (auto& pc : per_comm) {
+            std::vector<int> rots, evs;
+            for (auto& re : pc.second) { rots.push_back(re.first); evs.push_back(re.second); }
+            size_t j = 0;
+            while (j < sets.size() && sets[j].rots != rots) ++j;
+            if (j == sets.size()) {
+                RotSet s; s.rots = rots;
+                for (int r : superset) if (!pc.second.count(r)) s.diffs.push_back(r);
+                sets.push_back(s);
+            }
+            sets[j].comms.push_back(pc.first);
+            sets[j].evals.push_back(evs);
+        }
+        for (auto& s : sets) ZK_REQUIRE(s.rots.size() <= 4, "shplonk: more than 4 rotations in one set");
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// proving key (device resident) + reusable per-batch workspace
+// ---------------------------------------------------------------------------------------------
+struct HostPinned {
+    void* p = nullptr; size_t n = 0;
+    ~HostPinned() { if (p) cudaFreeHost(p); }
+    void ensure(size_t bytes) {
+        if (bytes <= n) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0;
+        ZK_CUDA(cudaMallocHost(&p, bytes));
+        n = bytes;
+    }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct ProverWs {
+    size_t B = 0;
+    DevBuf<fr_t> adv, inst, z, randp, adv_ext, z_ext, h, hpoly, comb, hx, lx, tmp1, tmp2, scratch, evals, low;
+    DevBuf<uint64_t> raw_adv, raw_z;
+    DevBuf<uint8_t> seeds;
+    DevBuf<Challenges> ch;
+    DevBuf<g1_affine_t> aff;
+    DevBuf<g1_xyzz_t> xyzz;
+    DevBuf<EvalJob> eval_jobs;
+    DevBuf<LinTerm> terms, terms2;
+    DevBuf<uint32_t> job_off, job_off2;
+    DevBuf<fr_t*> outs, outs2;
+    DevBuf<DivJob> div_jobs;
+    HostPinned h_aff, h_evals, h_stage;
+};
+
+struct PkEntry {
+    CsDesc cs;
+    uint64_t srs_handle = 0;
+    unsigned k = 0, ek = 0, A = 0, F = 0, S = 0, P = 0, Q = 0, bf = 0, chunk = 0;
+    size_t n = 0, en = 0, ustart = 0, num_evals = 0, proof_len = 0;
+    int rot_last = 0;
+    fr_t omega, omega_inv, ext_omega, ext_omega_inv, n_inv, en_inv, zeta, zeta_inv, digest;
+    DevBuf<fr_t> fixed_vals, fixed_polys, fixed_ext, sigma_vals, sigma_polys, sigma_ext, l0, l_last, l_active, t_inv, delta_pows, constants;
+    DevBuf<ColSrc> cols;
+    DevBuf<uint32_t> prog, gate_off;
+    DevBuf<int32_t> adv_q, fix_q, inst_q;
+    const fr_t* omega_tw = nullptr;
+    const fr_t* ext_tw = nullptr;
+    std::vector<g1_affine_t> fixed_commitments, perm_commitments;
+    QueryPlan plan;
+    ProverWs ws;
+};
+
+static std::map<uint64_t, std::unique_ptr<PkEntry>> g_pks;
+static uint64_t g_next_pk = 1;
+void prover_release_all() { g_pks.clear(); }
+
+static fr_t host_rotate(const PkEntry& pk, const fr_t& x, int rot) {
+    if (rot >= 0) return x * fr_pow_u64(pk.omega, (uint64_t)rot);
+    return x * fr_pow_u64(pk.omega_inv, (uint64_t)(-(long)rot));
+}
+static void host_batch_invert(std::vector<fr_t>& v) {
+    std::vector<fr_t> pre(v.size());
+    fr_t acc = fe_one<FrTag>();
+    for (size_t i = 0; i < v.size(); ++i) { pre[i] = acc; acc = acc * v[i]; }
+    acc = fe_inv(acc);
+    for (size_t i = v.size(); i-- > 0;) { fr_t t = acc * pre[i]; acc = acc * v[i]; v[i] = t; }
+}
+
+// ---- NTT helpers ----------------------------------------------------------------------------
+static const size_t SCRATCH_ELEMS = (size_t)1 << 25;  // 1 GiB of two-pass NTT scratch
+
+// lagrange_to_coeff on `count` contiguous polynomials of 2^k values, in place
+static void intt_n(PkEntry& pk, fr_t* p, size_t count, cudaStream_t st) {
+    ProverWs& W = pk.ws;
+    size_t per = pk.k > NTT_SINGLE_PASS_MAX_LOG ? std::max<size_t>(1, SCRATCH_ELEMS >> pk.k) : count;
+    if (pk.k > NTT_SINGLE_PASS_MAX_LOG) W.scratch.ensure(std::min(count, per) << pk.k);
+    for (size_t off = 0; off < count; off += per) {
+        NttJob J;
+        J.in = J.out = p + (off << pk.k); J.scratch = W.scratch.p; J.batch = std::min(per, count - off); J.log_n = pk.k;
+        J.omega = pk.omega_inv; J.has_scale = 1; J.scale = pk.n_inv;
+        ntt_run(J, st);
+    }
+}
+// coeff_to_extended: groups x cols polynomials at in[(g*cols + c)*n] -> out[g*out_group_stride + c*en]
+static void coset_ext(PkEntry& pk, const fr_t* in, fr_t* out, size_t groups, size_t cols, size_t out_group_stride, cudaStream_t st) {
+    ProverWs& W = pk.ws;
+    const bool two = pk.ek > NTT_SINGLE_PASS_MAX_LOG;
+    size_t per = two ? std::max<size_t>(1, (SCRATCH_ELEMS >> pk.ek) / cols) : groups;
+    if (two) W.scratch.ensure((std::min(groups, per) * cols) << pk.ek);
+    for (size_t off = 0; off < groups; off += per) {
+        size_t g = std::min(per, groups - off);
+        NttJob J;
+        J.in = in + off * cols * pk.n; J.out = out + off * out_group_stride; J.scratch = W.scratch.p;
+        J.batch = g * cols; J.log_n = pk.ek; J.omega = pk.ext_omega;
+        J.in_stride = pk.n; J.in_valid = pk.n; J.out_stride = pk.en;
+        J.out_inner = cols; J.out_outer_stride = out_group_stride;
+        J.pre_coset = 1; J.cs1 = pk.zeta; J.cs2 = pk.zeta_inv;
+        ntt_run(J, st);
+    }
+}
+// extended_to_coeff on `count` contiguous extended polynomials, in place (no truncation: callers read the prefix)
+static void coset_intt(PkEntry& pk, fr_t* p, size_t count, cudaStream_t st) {
+    ProverWs& W = pk.ws;
+    const bool two = pk.ek > NTT_SINGLE_PASS_MAX_LOG;
+    size_t per = two ? std::max<size_t>(1, SCRATCH_ELEMS >> pk.ek) : count;
+    if (two) W.scratch.ensure(std::min(count, per) << pk.ek);
+    for (size_t off = 0; off < count; off += per) {
+        NttJob J;
+        J.in = J.out = p + (off << pk.ek); J.scratch = W.scratch.p; J.batch = std::min(per, count - off); J.log_n = pk.ek;
+        J.omega = pk.ext_omega_inv; J.post_coset = 1; J.cs1 = pk.zeta_inv; J.cs2 = pk.zeta;
+        J.has_scale = 1; J.scale = pk.en_inv;
+        ntt_run(J, st);
+    }
+}
+// M commitments; MSM m reads scalars at (m / inner) * outer_stride + (m % inner) * n.  Affine out.
+static void commit(Context& C, PkEntry& pk, int basis, const fr_t* d_scalars, size_t M, size_t inner, size_t outer_stride,
+                   g1_affine_t* d_out, cudaStream_t st) {
+    SrsEntry& S = C.get_srs(pk.srs_handle);
+    MsmPlan plan = S.plan;
+    plan.n = pk.n; plan.tstride = S.n;
+    if (inner == 0) { inner = 1; outer_stride = pk.n; }
+    plan.inner = inner; plan.outer_stride = outer_stride;
+    size_t chunk = std::max<size_t>(inner, (1024 / inner) * inner);
+    pk.ws.xyzz.ensure(std::min(M, chunk));
+    for (size_t off = 0; off < M; off += chunk) {
+        size_t cnt = std::min(chunk, M - off);
+        msm_run(plan, d_scalars + (off / inner) * outer_stride, S.table[basis].p, cnt, pk.ws.xyzz.p, C.ws, st);
+        g1_normalize(pk.ws.xyzz.p, d_out + off, cnt, st);
+    }
+}
+
+template <class T>
+static void h2d(T* dst, const std::vector<T>& src, cudaStream_t st) {
+    if (!src.empty()) ZK_CUDA(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+template <class T>
+static void upload(DevBuf<T>& buf, const std::vector<T>& src, cudaStream_t st) {
+    buf.ensure(std::max<size_t>(1, src.size()));
+    h2d(buf.p, src, st);
+}
+
+static void trace_dev(const char* name, const fr_t* d, size_t count, size_t reps, size_t stride, cudaStream_t st) {
+    if (!g_trace) return;
+    std::vector<fr_t> h(count);
+    for (size_t r = 0; r < reps; ++r) {
+        ZK_CUDA(cudaMemcpyAsync(h.data(), d + r * stride, count * sizeof(fr_t), cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(cudaStreamSynchronize(st));
+        g_trace(name, h.data(), count * sizeof(fr_t));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// keygen_vk + keygen_pk
+// ---------------------------------------------------------------------------------------------
+static std::unique_ptr<PkEntry> keygen(Context& C, uint64_t srs_handle, const uint8_t* blob, size_t len) {
+    std::unique_ptr<PkEntry> pkp(new PkEntry);
+    PkEntry& pk = *pkp;
+    pk.cs = CsDesc::parse(blob, len);
+    const CsDesc& cs = pk.cs;
+    SrsEntry& S = C.get_srs(srs_handle);
+    ZK_REQUIRE(S.k == cs.k, "keygen: params.k != circuit k (downsize the params first)");
+    pk.srs_handle = srs_handle;
+    pk.k = cs.k; pk.n = cs.n(); pk.ek = cs.extended_k(); pk.en = (size_t)1 << pk.ek;
+    pk.A = cs.num_advice; pk.F = cs.num_fixed; pk.S = (unsigned)cs.perm_columns.size(); pk.P = cs.num_perm_sets(); pk.Q = cs.num_quotients();
+    pk.bf = cs.blinding_factors(); pk.chunk = cs.chunk_len(); pk.ustart = cs.unusable_start(); pk.rot_last = cs.rotation_last();
+    pk.num_evals = cs.num_evals(); pk.proof_len = cs.proof_len();
+    ZK_REQUIRE(pk.ek <= 24, "keygen: extended domain too large");
+    ZK_REQUIRE(pk.bf + 1 < pk.n, "keygen: not enough rows");
+    pk.omega = fr_omega(pk.k); pk.omega_inv = fr_omega_inv(pk.k);
+    pk.ext_omega = fr_omega(pk.ek); pk.ext_omega_inv = fr_omega_inv(pk.ek);
+    pk.n_inv = fr_pow2_inv(pk.k); pk.en_inv = fr_pow2_inv(pk.ek);
+    pk.zeta = fr_from_limbs(fr_consts::ZETA); pk.zeta_inv = fr_from_limbs(fr_consts::ZETA_INV);
+    pk.plan.build(cs);
+    cudaStream_t st = C.stream;
+    const size_t n = pk.n, en = pk.en;
+    pk.omega_tw = ntt_twiddles(pk.k, pk.omega, st);
+    pk.ext_tw = ntt_twiddles(pk.ek, pk.ext_omega, st);
+
+    auto commit_cols = [&](const fr_t* d_vals, size_t count, std::vector<g1_affine_t>& out) {
+        out.resize(count);
+        if (!count) return;
+        pk.ws.aff.ensure(count);
+        commit(C, pk, 1, d_vals, count, 0, 0, pk.ws.aff.p, st);
+        ZK_CUDA(cudaMemcpyAsync(out.data(), pk.ws.aff.p, count * sizeof(g1_affine_t), cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(cudaStreamSynchronize(st));
+    };
+    auto polys_and_cosets = [&](const DevBuf<fr_t>& vals, DevBuf<fr_t>& polys, DevBuf<fr_t>& ext, size_t count) {
+        polys.alloc(std::max<size_t>(1, count * n)); ext.alloc(std::max<size_t>(1, count * en));
+        if (!count) return;
+        ZK_CUDA(cudaMemcpyAsync(polys.p, vals.p, count * n * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+        intt_n(pk, polys.p, count, st);
+        coset_ext(pk, polys.p, ext.p, 1, count, count * en, st);
+    };
+    // fixed columns
+    pk.fixed_vals.alloc(std::max<size_t>(1, pk.F * n));
+    h2d(pk.fixed_vals.p, cs.fixed, st);
+    commit_cols(pk.fixed_vals.p, pk.F, pk.fixed_commitments);
+    polys_and_cosets(pk.fixed_vals, pk.fixed_polys, pk.fixed_ext, pk.F);
+    // permutation: sigma columns hold delta^col * omega^row of the mapped cell
+    {
+        PermAssembly as(pk.S, n);
+        for (auto& cp : cs.copies) as.copy(cp.lcol, cp.lrow, cp.rcol, cp.rrow);
+        std::vector<fr_t> dp(std::max<unsigned>(1, pk.S));
+        fr_t d = fe_one<FrTag>(), delta = fr_from_limbs(fr_consts::DELTA);
+        for (unsigned c = 0; c < pk.S; ++c) { dp[c] = d; d = d * delta; }
+        upload(pk.delta_pows, dp, st);
+        DevBuf<uint32_t> d_mc(std::max<size_t>(1, as.map_col.size())), d_mr(std::max<size_t>(1, as.map_row.size()));
+        h2d(d_mc.p, as.map_col, st); h2d(d_mr.p, as.map_row, st);
+        pk.sigma_vals.alloc(std::max<size_t>(1, pk.S * n));
+        launch_sigma_values(d_mc.p, d_mr.p, pk.delta_pows.p, pk.omega_tw, pk.sigma_vals.p, pk.S, pk.k, st);
+        ZK_CUDA(cudaStreamSynchronize(st));
+        commit_cols(pk.sigma_vals.p, pk.S, pk.perm_commitments);
+        polys_and_cosets(pk.sigma_vals, pk.sigma_polys, pk.sigma_ext, pk.S);
+        std::vector<ColSrc> cols(std::max<unsigned>(1, pk.S));
+        for (unsigned c = 0; c < pk.S; ++c) { cols[c].type = cs.perm_columns[c].type; cols[c].index = cs.perm_columns[c].index; }
+        upload(pk.cols, cols, st);
+    }
+    // l_0, l_blind, l_last on the extended coset; l_active_row = 1 - l_last - l_blind
+    {
+        std::vector<fr_t> lag(3 * n, fr_t::zero());
+        fr_t one = fe_one<FrTag>();
+        lag[0] = one;
+        for (size_t i = n - pk.bf; i < n; ++i) lag[n + i] = one;
+        lag[2 * n + (n - pk.bf - 1)] = one;
+        DevBuf<fr_t> vals(3 * n), polys, ext;
+        h2d(vals.p, lag, st);
+        polys_and_cosets(vals, polys, ext, 3);
+        pk.l0.alloc(en); pk.l_last.alloc(en); pk.l_active.alloc(en);
+        ZK_CUDA(cudaMemcpyAsync(pk.l0.p, ext.p, en * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+        ZK_CUDA(cudaMemcpyAsync(pk.l_last.p, ext.p + 2 * en, en * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+        launch_one_minus_sum(ext.p + 2 * en, ext.p + en, pk.l_active.p, en, st);
+        ZK_CUDA(cudaStreamSynchronize(st));
+    }
+    // t_evaluations (inverted): ((zeta * ext_omega^i)^n - 1)^-1, i < 2^(ek-k)
+    {
+        size_t tcount = (size_t)1 << (pk.ek - pk.k);
+        std::vector<fr_t> t(tcount);
+        fr_t cur = fr_pow_u64(pk.zeta, n), step = fr_pow_u64(pk.ext_omega, n), one = fe_one<FrTag>();
+        for (size_t i = 0; i < tcount; ++i) { t[i] = cur - one; cur = cur * step; }
+        host_batch_invert(t);
+        upload(pk.t_inv, t, st);
+    }
+    // gate programs
+    {
+        std::vector<uint32_t> prog, off{0};
+        for (auto& g : cs.gates) {
+            for (auto& i : g) { prog.push_back(i.op); prog.push_back(i.arg); }
+            off.push_back((uint32_t)(prog.size() / 2));
+        }
+        if (prog.empty()) prog.assign(2, 0);
+        upload(pk.prog, prog, st); upload(pk.gate_off, off, st);
+        std::vector<fr_t> consts = cs.constants;
+        if (consts.empty()) consts.push_back(fr_t::zero());
+        upload(pk.constants, consts, st);
+        auto qv = [](const std::vector<QueryRef>& q) {
+            std::vector<int32_t> v;
+            for (auto& e : q) { v.push_back((int32_t)e.column); v.push_back(e.rotation); }
+            if (v.empty()) v.assign(2, 0);
+            return v;
+        };
+        upload(pk.adv_q, qv(cs.advice_queries), st); upload(pk.fix_q, qv(cs.fixed_queries), st); upload(pk.inst_q, qv(cs.instance_queries), st);
+        ZK_CUDA(cudaStreamSynchronize(st));
+    }
+    // opaque vk digest (see oracle/plonk.hpp header): keccak(blob ‖ fixed commitments ‖ sigma commitments) mod r
+    {
+        std::vector<uint8_t> in(cs.blob);
+        auto add = [&](const g1_affine_t& p) { uint8_t w[64]; fe_to_be_bytes(p.x, w); fe_to_be_bytes(p.y, w + 32); in.insert(in.end(), w, w + 64); };
+        for (auto& p : pk.fixed_commitments) add(p);
+        for (auto& p : pk.perm_commitments) add(p);
+        uint8_t h[32]; keccak256(in.data(), in.size(), h);
+        pk.digest = fr_from_be_bytes_reduce(h);
+    }
+    return pkp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// create_proof for a sub-batch of B proofs
+// ---------------------------------------------------------------------------------------------
+struct ProofState {
+    Transcript tr;
+    fr_t beta, gamma, y, x, xn, zeta, nu, mu;
+    std::vector<fr_t> evals;                 // num_evals + 1 (quotient eval last)
+    std::vector<fr_t> points;                // x * omega^r for r in superset
+    std::vector<std::vector<fr_t>> rcomb;    // per set: low-degree remainder coefficients
+    explicit ProofState(uint8_t* out) : tr(out) {}
+};
+
+static size_t default_batch(const PkEntry& pk) {
+    if (const char* e = getenv("ZKGPU_PROVER_BATCH")) { long v = atol(e); if (v > 0) return (size_t)v; }
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    size_t per = ((size_t)(pk.A + 1 + pk.P + 1) * pk.en + (size_t)(pk.A + 2 * pk.P + 8 + 3 * pk.plan.sets.size()) * pk.n) * sizeof(fr_t);
+    size_t B = (size_t)(free_b * 0.35) / std::max<size_t>(per, 1);
+    return std::max<size_t>(1, std::min<size_t>(B, 128));
+}
+
+static void ensure_ws(PkEntry& pk, size_t B) {
+    ProverWs& W = pk.ws;
+    const size_t n = pk.n, en = pk.en, ns = pk.plan.sets.size();
+    W.B = std::max(W.B, B);
+    W.adv.ensure(B * pk.A * n); W.inst.ensure(B * n); W.z.ensure(std::max<size_t>(1, B * pk.P * n)); W.randp.ensure(B * n);
+    W.adv_ext.ensure(B * (pk.A + 1) * en); W.z_ext.ensure(std::max<size_t>(1, B * pk.P * en)); W.h.ensure(B * en);
+    W.hpoly.ensure(B * n); W.comb.ensure(B * ns * n); W.hx.ensure(B * n); W.lx.ensure(B * n);
+    W.tmp1.ensure(B * ns * n); W.tmp2.ensure(B * ns * n);
+    W.evals.ensure(B * (pk.num_evals + 1)); W.low.ensure(B * (ns + 1) * 4);
+    W.raw_adv.ensure(std::max<size_t>(1, B * pk.A * (pk.bf + 1) * 8)); W.raw_z.ensure(std::max<size_t>(1, B * pk.P * pk.bf * 8));
+    W.seeds.ensure(B * 32); W.ch.ensure(B);
+    size_t max_pts = B * std::max<size_t>(std::max<size_t>(pk.A, pk.P + 1), std::max<size_t>(pk.Q, 1));
+    W.aff.ensure(max_pts);
+    W.h_aff.ensure(max_pts * sizeof(g1_affine_t)); W.h_evals.ensure(B * (pk.num_evals + 1) * sizeof(fr_t));
+    ZK_REQUIRE(2 * B * pk.P * n <= B * (pk.A + 1) * en, "workspace aliasing assumption violated");
+}
+
+static void prove_sub_batch(Context& C, PkEntry& pk, const fr_t* advice, bool advice_on_device, const fr_t* instance, size_t num_pi,
+                            size_t B, const uint64_t* seeds, uint8_t* proofs) {
+    ProverWs& W = pk.ws;
+    const CsDesc& cs = pk.cs;
+    cudaStream_t st = C.stream;
+    const size_t n = pk.n, en = pk.en, A = pk.A, P = pk.P, Q = pk.Q, bf = pk.bf;
+    const size_t ns = pk.plan.sets.size();
+    ensure_ws(pk, B);
+    const fr_t one = fe_one<FrTag>();
+
+    StepTimer timer;
+    // ---- step 0: transcripts, RNG streams, uploads ------------------------------------------
+    std::vector<ProofState> ps;
+    ps.reserve(B);
+    std::vector<uint64_t> raw_adv(B * A * (bf + 1) * 8), raw_z(B * P * bf * 8);
+    std::vector<uint8_t> cseeds(B * 32);
+    for (size_t b = 0; b < B; ++b) {
+        ps.emplace_back(proofs + b * pk.proof_len);
+        ProofState& p = ps.back();
+        p.tr.common_scalar(pk.digest);
+        for (size_t i = 0; i < num_pi; ++i) p.tr.common_scalar(instance[b * num_pi + i]);
+        SmallRng rng(seeds[b]);
+        // advice blinding rows column by column, then one unused Blind per column
+        for (size_t t = 0; t < A * (bf + 1); ++t) rng.next_wide(&raw_adv[(b * A * (bf + 1) + t) * 8]);
+        for (size_t c = 0; c < A; ++c) rng.skip_wide();
+        // permutation: per set bf blinding rows, then its unused Blind
+        for (size_t s = 0; s < P; ++s) {
+            for (size_t t = 0; t < bf; ++t) rng.next_wide(&raw_z[((b * P + s) * bf + t) * 8]);
+            rng.skip_wide();
+        }
+        // vanishing: ChaCha20 seed for the random polynomial, its Blind; quotient piece Blinds follow (unused)
+        rng.fill_bytes32(&cseeds[b * 32]);
+    }
+    if (advice_on_device) ZK_CUDA(cudaMemcpyAsync(W.adv.p, advice, B * A * n * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+    else ZK_CUDA(cudaMemcpyAsync(W.adv.p, advice, B * A * n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+    ZK_CUDA(cudaMemsetAsync(W.inst.p, 0, B * n * sizeof(fr_t), st));
+    if (num_pi)
+        ZK_CUDA(cudaMemcpy2DAsync(W.inst.p, n * sizeof(fr_t), instance, num_pi * sizeof(fr_t), num_pi * sizeof(fr_t), B, cudaMemcpyHostToDevice, st));
+    h2d(W.raw_adv.p, raw_adv, st); h2d(W.raw_z.p, raw_z, st); h2d(W.seeds.p, cseeds, st);
+
+    auto fetch_points = [&](size_t count) -> const g1_affine_t* {
+        ZK_CUDA(cudaMemcpyAsync(W.h_aff.p, W.aff.p, count * sizeof(g1_affine_t), cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(cudaStreamSynchronize(st));
+        return W.h_aff.as<g1_affine_t>();
+    };
+    std::vector<Challenges> ch(B);
+    auto push_challenges = [&]() {
+        for (size_t b = 0; b < B; ++b) { ch[b].beta = ps[b].beta; ch[b].gamma = ps[b].gamma; ch[b].y = ps[b].y; ch[b].x = ps[b].x; }
+        h2d(W.ch.p, ch, st);
+    };
+
+    timer.lap(0);
+    // ---- step 1: blind + commit advice --------------------------------------------------------
+    launch_scatter_random(W.adv.p, A * n, n, pk.ustart, W.raw_adv.p, B, A, bf + 1, st);
+    trace_dev("advice_blinded", W.adv.p, n, A, n, st);
+    commit(C, pk, 1, W.adv.p, B * A, 0, 0, W.aff.p, st);
+    {
+        const g1_affine_t* pts = fetch_points(B * A);
+        for (size_t b = 0; b < B; ++b) {
+            for (size_t c = 0; c < A; ++c) ps[b].tr.write_point(pts[b * A + c]);
+            (void)ps[b].tr.squeeze();  // theta (no lookups)
+            ps[b].beta = ps[b].tr.squeeze(); ps[b].gamma = ps[b].tr.squeeze();
+            ps[b].y = fr_t::zero(); ps[b].x = fr_t::zero();
+        }
+    }
+    push_challenges();
+
+    timer.lap(1);
+    // ---- step 2: permutation grand products, random polynomial --------------------------------
+    if (P) {
+        fr_t* num = W.adv_ext.p; fr_t* den = W.adv_ext.p + B * P * n;  // adv_ext is free until step 4
+        PermArgs pa;
+        pa.adv = W.adv.p; pa.adv_proof_stride = A * n; pa.inst = W.inst.p; pa.inst_proof_stride = n;
+        pa.fixed_vals = pk.fixed_vals.p; pa.sigma_vals = pk.sigma_vals.p; pa.cols = pk.cols.p; pa.delta_pows = pk.delta_pows.p;
+        pa.omega_tw = pk.omega_tw; pa.ch = W.ch.p; pa.k = pk.k; pa.S = pk.S; pa.chunk = pk.chunk; pa.P = pk.P;
+        launch_perm_num_den(pa, num, den, B, st);
+        launch_batch_inverse(den, B * P * n, st);
+        launch_perm_scan(num, den, W.z.p, pk.k, B * P, st);
+        launch_perm_finalize(W.z.p, pk.k, pk.P, pk.bf, W.raw_z.p, B, st);
+        trace_dev("z", W.z.p, n, P, n, st);
+        commit(C, pk, 1, W.z.p, B * P, 0, 0, W.aff.p, st);
+    }
+    launch_chacha_poly(W.seeds.p, W.randp.p, n, B, st);
+    trace_dev("random_poly", W.randp.p, n, 1, n, st);
+    commit(C, pk, 0, W.randp.p, B, 0, 0, W.aff.p + B * P, st);
+    ZK_CUDA(cudaMemcpyAsync(W.h_aff.p, W.aff.p, B * (P + 1) * sizeof(g1_affine_t), cudaMemcpyDeviceToHost, st));
+    cudaEvent_t ev_pts;
+    ZK_CUDA(cudaEventCreateWithFlags(&ev_pts, cudaEventDisableTiming));
+    ZK_CUDA(cudaEventRecord(ev_pts, st));
+    // queue the transforms that do not depend on y behind the commitments
+    if (P) {
+        intt_n(pk, W.z.p, B * P, st);
+        coset_ext(pk, W.z.p, W.z_ext.p, B, P, P * en, st);
+    }
+    intt_n(pk, W.adv.p, B * A, st);
+    intt_n(pk, W.inst.p, B, st);
+    coset_ext(pk, W.adv.p, W.adv_ext.p, B, A, (A + 1) * en, st);
+    coset_ext(pk, W.inst.p, W.adv_ext.p + A * en, B, 1, (A + 1) * en, st);
+    ZK_CUDA(cudaEventSynchronize(ev_pts));
+    ZK_CUDA(cudaEventDestroy(ev_pts));
+    {
+        const g1_affine_t* pts = W.h_aff.as<g1_affine_t>();
+        for (size_t b = 0; b < B; ++b) {
+            for (size_t s = 0; s < P; ++s) ps[b].tr.write_point(pts[b * P + s]);
+            ps[b].tr.write_point(pts[B * P + b]);
+            ps[b].y = ps[b].tr.squeeze();
+        }
+    }
+    push_challenges();
+    trace_dev("advice_poly", W.adv.p, n, A, n, st);
+    trace_dev("z_poly", W.z.p, n, P, n, st);
+    trace_dev("z_coset", W.z_ext.p, en, P, en, st);
+    trace_dev("advice_coset", W.adv_ext.p, en, A, en, st);
+    trace_dev("instance_coset", W.adv_ext.p + A * en, en, 1, en, st);
+
+    timer.lap(2);
+    // ---- step 3: quotient ---------------------------------------------------------------------
+    {
+        EvalHArgs ea;
+        ea.adv_ext = W.adv_ext.p; ea.adv_ext_proof_stride = (A + 1) * en; ea.z_ext = W.z_ext.p; ea.z_ext_proof_stride = P * en;
+        ea.fixed_ext = pk.fixed_ext.p; ea.sigma_ext = pk.sigma_ext.p; ea.l0 = pk.l0.p; ea.l_last = pk.l_last.p; ea.l_active = pk.l_active.p;
+        ea.t_inv = pk.t_inv.p; ea.ext_tw = pk.ext_tw; ea.delta_pows = pk.delta_pows.p; ea.cols = pk.cols.p; ea.ch = W.ch.p;
+        ea.prog = pk.prog.p; ea.gate_off = pk.gate_off.p; ea.constants = pk.constants.p;
+        ea.adv_q = pk.adv_q.p; ea.fix_q = pk.fix_q.p; ea.inst_q = pk.inst_q.p;
+        ea.num_gates = (unsigned)cs.gates.size(); ea.A = pk.A; ea.S = pk.S; ea.chunk = pk.chunk; ea.P = pk.P; ea.k = pk.k; ea.ek = pk.ek;
+        ea.rotation_last = pk.rot_last; ea.zeta = pk.zeta;
+        launch_eval_h(ea, W.h.p, B, st);
+    }
+    trace_dev("h_evals", W.h.p, en, 1, en, st);
+    coset_intt(pk, W.h.p, B, st);
+    trace_dev("h_coeffs", W.h.p, Q * n, 1, en, st);
+    commit(C, pk, 0, W.h.p, B * Q, Q, en, W.aff.p, st);
+    {
+        const g1_affine_t* pts = fetch_points(B * Q);
+        for (size_t b = 0; b < B; ++b) {
+            for (size_t i = 0; i < Q; ++i) ps[b].tr.write_point(pts[b * Q + i]);
+            ps[b].x = ps[b].tr.squeeze();
+            ps[b].xn = ps[b].x;
+            for (unsigned i = 0; i < pk.k; ++i) ps[b].xn = sqr(ps[b].xn);
+        }
+    }
+
+    timer.lap(3);
+    // ---- step 4: evaluations ------------------------------------------------------------------
+    const size_t NE = pk.num_evals;
+    {
+        // h(X) = sum_i xn^i * piece_i
+        std::vector<LinTerm> terms(B * Q);
+        std::vector<uint32_t> off(B + 1);
+        std::vector<fr_t*> outs(B);
+        for (size_t b = 0; b < B; ++b) {
+            fr_t c = one;
+            off[b] = (uint32_t)(b * Q);
+            for (size_t i = 0; i < Q; ++i) { terms[b * Q + i].poly = W.h.p + b * en + i * n; terms[b * Q + i].coef = c; c = c * ps[b].xn; }
+            outs[b] = W.hpoly.p + b * n;
+        }
+        off[B] = (uint32_t)(B * Q);
+        upload(W.terms, terms, st); upload(W.job_off, off, st); upload(W.outs, outs, st);
+        launch_lincomb(W.terms.p, W.job_off.p, W.outs.p, B, n, st);
+
+        std::vector<EvalJob> jobs(B * (NE + 1));
+        for (size_t b = 0; b < B; ++b) {
+            ProofState& p = ps[b];
+            EvalJob* j = &jobs[b * (NE + 1)];
+            const fr_t x = p.x;
+            std::map<int, fr_t> rx;
+            auto at = [&](int r) -> const fr_t& {
+                auto it = rx.find(r);
+                if (it == rx.end()) it = rx.emplace(r, host_rotate(pk, x, r)).first;
+                return it->second;
+            };
+            for (auto& q : cs.advice_queries) { j->poly = W.adv.p + (b * A + q.column) * n; j->x = at(q.rotation); ++j; }
+            for (auto& q : cs.fixed_queries) { j->poly = pk.fixed_polys.p + (size_t)q.column * n; j->x = at(q.rotation); ++j; }
+            j->poly = W.randp.p + b * n; j->x = x; ++j;
+            for (size_t c = 0; c < pk.S; ++c) { j->poly = pk.sigma_polys.p + c * n; j->x = x; ++j; }
+            for (size_t s = 0; s < P; ++s) {
+                const fr_t* zp = W.z.p + (b * P + s) * n;
+                j->poly = zp; j->x = x; ++j;
+                j->poly = zp; j->x = at(1); ++j;
+                if (s + 1 < P) { j->poly = zp; j->x = at(pk.rot_last); ++j; }
+            }
+            j->poly = W.hpoly.p + b * n; j->x = x; ++j;  // quotient evaluation: computed, not written
+            ZK_REQUIRE((size_t)(j - &jobs[b * (NE + 1)]) == NE + 1, "internal: evaluation count mismatch");
+            p.points.clear();
+            for (int r : pk.plan.superset) p.points.push_back(at(r));
+        }
+        upload(W.eval_jobs, jobs, st);
+        launch_poly_eval(W.eval_jobs.p, W.evals.p, jobs.size(), pk.k, st);
+        ZK_CUDA(cudaMemcpyAsync(W.h_evals.p, W.evals.p, jobs.size() * sizeof(fr_t), cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(cudaStreamSynchronize(st));
+        const fr_t* he = W.h_evals.as<fr_t>();
+        for (size_t b = 0; b < B; ++b) {
+            ProofState& p = ps[b];
+            p.evals.assign(he + b * (NE + 1), he + (b + 1) * (NE + 1));
+            for (size_t i = 0; i < NE; ++i) p.tr.write_scalar(p.evals[i]);
+            p.zeta = p.tr.squeeze(); p.nu = p.tr.squeeze();
+        }
+        if (g_trace) { g_trace("evals", ps[0].evals.data(), NE * sizeof(fr_t)); }
+        trace_dev("h_poly", W.hpoly.p, n, 1, n, st);
+    }
+
+    timer.lap(4);
+    // ---- step 5: SHPLONK h(X) -----------------------------------------------------------------
+    auto poly_of = [&](size_t b, int id) -> const fr_t* {
+        if (id < pk.plan.id_z0) return W.adv.p + (b * A + id) * n;
+        if (id < pk.plan.id_fixed0) return W.z.p + (b * P + (id - pk.plan.id_z0)) * n;
+        if (id < pk.plan.id_sigma0) return pk.fixed_polys.p + (size_t)(id - pk.plan.id_fixed0) * n;
+        if (id < pk.plan.id_h) return pk.sigma_polys.p + (size_t)(id - pk.plan.id_sigma0) * n;
+        return id == pk.plan.id_h ? W.hpoly.p + b * n : W.randp.p + b * n;
+    };
+    auto point_of = [&](const ProofState& p, int rot) -> const fr_t& {
+        for (size_t i = 0; i < pk.plan.superset.size(); ++i) if (pk.plan.superset[i] == rot) return p.points[i];
+        throw Error(ZK_ERR_INTERNAL, "rotation not in the superset");
+    };
+    std::vector<const fr_t*> set_num(B * ns);  // quotient of each set after its divisions
+    {
+        std::vector<LinTerm> terms;
+        std::vector<uint32_t> off;
+        std::vector<fr_t*> outs;
+        std::vector<fr_t> low(B * ns * 4, fr_t::zero());
+        std::vector<std::vector<DivJob>> rounds(4);
+        for (size_t b = 0; b < B; ++b) {
+            ProofState& p = ps[b];
+            p.rcomb.assign(ns, {});
+            // denominators of the Lagrange basis of every set, inverted together
+            std::vector<fr_t> dens;
+            for (auto& s : pk.plan.sets)
+                for (size_t j = 0; j < s.rots.size(); ++j) {
+                    fr_t d = one;
+                    for (size_t t = 0; t < s.rots.size(); ++t) if (t != j) d = d * (point_of(p, s.rots[j]) - point_of(p, s.rots[t]));
+                    dens.push_back(d);
+                }
+            host_batch_invert(dens);
+            size_t di = 0;
+            for (size_t si = 0; si < ns; ++si) {
+                const RotSet& s = pk.plan.sets[si];
+                const size_t m = s.rots.size();
+                off.push_back((uint32_t)terms.size());
+                std::vector<fr_t> w(m, fr_t::zero());  // sum_c zeta^c * eval_{c, rot j}
+                fr_t zp = one;
+                for (size_t c = 0; c < s.comms.size(); ++c) {
+                    LinTerm t; t.poly = poly_of(b, s.comms[c]); t.coef = zp;
+                    terms.push_back(t);
+                    for (size_t j = 0; j < m; ++j) w[j] = w[j] + zp * p.evals[s.evals[c][j]];
+                    zp = zp * p.zeta;
+                }
+                outs.push_back(W.comb.p + (b * ns + si) * n);
+                // r(X) = sum_j w_j / den_j * prod_{t != j} (X - x_t)
+                std::vector<fr_t> r(m, fr_t::zero());
+                for (size_t j = 0; j < m; ++j) {
+                    std::vector<fr_t> np{one};
+                    for (size_t t = 0; t < m; ++t) {
+                        if (t == j) continue;
+                        const fr_t& xt = point_of(p, s.rots[t]);
+                        std::vector<fr_t> nn(np.size() + 1, fr_t::zero());
+                        for (size_t u = 0; u < np.size(); ++u) { nn[u + 1] = nn[u + 1] + np[u]; nn[u] = nn[u] - np[u] * xt; }
+                        np.swap(nn);
+                    }
+                    fr_t sc = w[j] * dens[di + j];
+                    for (size_t u = 0; u < m; ++u) r[u] = r[u] + np[u] * sc;
+                }
+                di += m;
+                for (size_t u = 0; u < m; ++u) low[(b * ns + si) * 4 + u] = r[u];
+                p.rcomb[si] = r;
+                // divisions by (X - x_t), ping-pong between tmp1 / tmp2
+                const fr_t* cur = W.comb.p + (b * ns + si) * n;
+                for (size_t t = 0; t < m; ++t) {
+                    DivJob dj;
+                    dj.in = cur; dj.out = ((t & 1) ? W.tmp2.p : W.tmp1.p) + (b * ns + si) * n; dj.pt = point_of(p, s.rots[t]);
+                    dj.low = t == 0 ? W.low.p + (b * ns + si) * 4 : nullptr;
+                    rounds[t].push_back(dj);
+                    cur = dj.out;
+                }
+                set_num[b * ns + si] = cur;
+            }
+        }
+        off.push_back((uint32_t)terms.size());
+        upload(W.terms, terms, st); upload(W.job_off, off, st); upload(W.outs, outs, st);
+        h2d(W.low.p, low, st);
+        launch_lincomb(W.terms.p, W.job_off.p, W.outs.p, B * ns, n, st);
+        trace_dev("set_combined", W.comb.p, n, ns, n, st);
+        size_t total_div = 0;
+        for (auto& r : rounds) total_div += r.size();
+        W.div_jobs.ensure(std::max<size_t>(1, total_div));
+        size_t doff = 0;
+        for (auto& r : rounds) {
+            if (r.empty()) continue;
+            h2d(W.div_jobs.p + doff, r, st);
+            launch_kate_div(W.div_jobs.p + doff, r.size(), pk.k, st);
+            doff += r.size();
+        }
+        // h(X) = sum_i nu^i * num_i(X)
+        std::vector<LinTerm> t2(B * ns);
+        std::vector<uint32_t> off2(B + 1);
+        std::vector<fr_t*> outs2(B);
+        for (size_t b = 0; b < B; ++b) {
+            fr_t np = one;
+            off2[b] = (uint32_t)(b * ns);
+            for (size_t si = 0; si < ns; ++si) { t2[b * ns + si].poly = set_num[b * ns + si]; t2[b * ns + si].coef = np; np = np * ps[b].nu; }
+            outs2[b] = W.hx.p + b * n;
+        }
+        off2[B] = (uint32_t)(B * ns);
+        upload(W.terms2, t2, st); upload(W.job_off2, off2, st); upload(W.outs2, outs2, st);
+        launch_lincomb(W.terms2.p, W.job_off2.p, W.outs2.p, B, n, st);
+        trace_dev("hx", W.hx.p, n, 1, n, st);
+        commit(C, pk, 0, W.hx.p, B, 0, 0, W.aff.p, st);
+        const g1_affine_t* pts = fetch_points(B);
+        for (size_t b = 0; b < B; ++b) { ps[b].tr.write_point(pts[b]); ps[b].mu = ps[b].tr.squeeze(); }
+    }
+
+    timer.lap(5);
+    // ---- step 6: SHPLONK linearisation L(X) / (X - mu) ----------------------------------------
+    {
+        std::vector<LinTerm> terms(B * (ns + 1));
+        std::vector<uint32_t> off(B + 1);
+        std::vector<fr_t*> outs(B);
+        std::vector<fr_t> low(B * 4, fr_t::zero());
+        std::vector<DivJob> divs(B);
+        for (size_t b = 0; b < B; ++b) {
+            ProofState& p = ps[b];
+            auto zeval = [&](const std::vector<int>& rots) { fr_t a = one; for (int r : rots) a = a * (p.mu - point_of(p, r)); return a; };
+            fr_t z_t = zeval(pk.plan.superset);
+            std::vector<fr_t> zd(ns);
+            for (size_t si = 0; si < ns; ++si) zd[si] = zeval(pk.plan.sets[si].diffs);
+            fr_t zd0_inv = fe_inv(zd[0]);
+            fr_t np = one, K = fr_t::zero();
+            off[b] = (uint32_t)(b * (ns + 1));
+            for (size_t si = 0; si < ns; ++si) {
+                fr_t sc = np * zd[si];
+                // r_i(mu)
+                fr_t rm = fr_t::zero();
+                for (size_t u = p.rcomb[si].size(); u-- > 0;) rm = rm * p.mu + p.rcomb[si][u];
+                K = K + rm * sc;
+                terms[b * (ns + 1) + si].poly = W.comb.p + (b * ns + si) * n;
+                terms[b * (ns + 1) + si].coef = sc * zd0_inv;
+                np = np * p.nu;
+            }
+            terms[b * (ns + 1) + ns].poly = W.hx.p + b * n;
+            terms[b * (ns + 1) + ns].coef = neg(z_t * zd0_inv);
+            low[b * 4] = K * zd0_inv;
+            outs[b] = W.lx.p + b * n;
+            divs[b].in = W.lx.p + b * n; divs[b].out = W.tmp1.p + b * n; divs[b].pt = p.mu; divs[b].low = W.low.p + b * 4;
+        }
+        off[B] = (uint32_t)(B * (ns + 1));
+        upload(W.terms, terms, st); upload(W.job_off, off, st); upload(W.outs, outs, st);
+        h2d(W.low.p, low, st);
+        launch_lincomb(W.terms.p, W.job_off.p, W.outs.p, B, n, st);
+        W.div_jobs.ensure(B);
+        h2d(W.div_jobs.p, divs, st);
+        launch_kate_div(W.div_jobs.p, B, pk.k, st);
+        trace_dev("wq", W.tmp1.p, n, 1, n, st);
+        commit(C, pk, 0, W.tmp1.p, B, 0, 0, W.aff.p, st);
+        const g1_affine_t* pts = fetch_points(B);
+        for (size_t b = 0; b < B; ++b) {
+            ps[b].tr.write_point(pts[b]);
+            ZK_REQUIRE((size_t)(ps[b].tr.out - (proofs + b * pk.proof_len)) == pk.proof_len, "internal: proof length mismatch");
+        }
+    }
+    timer.lap(6);
+}
+
+static void prove_batch(uint64_t handle, const uint64_t* advice, bool advice_on_device, const uint64_t* instance, size_t num_pi, size_t m,
+                        const uint64_t* seeds, uint8_t* proofs, size_t proof_len) {
+    Context& C = ctx(); C.require();
+    auto it = g_pks.find(handle);
+    ZK_REQUIRE(it != g_pks.end(), "unknown proving key handle");
+    PkEntry& pk = *it->second;
+    ZK_REQUIRE(proof_len == pk.proof_len, "prove: proof_len does not match the circuit (see zkgpu_pk_info)");
+    ZK_REQUIRE(m == 0 || (advice && seeds && proofs), "null pointer");
+    ZK_REQUIRE(num_pi == 0 || instance, "null pointer");
+    ZK_REQUIRE(num_pi <= pk.ustart, "prove: InstanceTooLarge");
+    size_t Bmax = default_batch(pk);
+    for (size_t off = 0; off < m; off += Bmax) {
+        size_t B = std::min(Bmax, m - off);
+        prove_sub_batch(C, pk, reinterpret_cast<const fr_t*>(advice) + off * pk.A * pk.n, advice_on_device,
+                        reinterpret_cast<const fr_t*>(instance) + off * num_pi, num_pi, B, seeds + off, proofs + off * proof_len);
+    }
+}
+
+}  // namespace zk
+
+using namespace zk;
+
+#define API_BEGIN try { std::lock_guard<std::recursive_mutex> lk_(ctx().mu);
+#define API_END                                                           \
+    return ZKGPU_OK; }                                                    \
+    catch (const zk::Error& e) { g_last_error = e.what(); return e.code; } \
+    catch (const std::exception& e) { g_last_error = e.what(); return ZKGPU_ERR_INTERNAL; }
+
+extern "C" {
+
+void zkgpu_prover_step_seconds(double out[8], int reset) {
+    for (int i = 0; i < 8; ++i) { out[i] = g_step_s[i]; if (reset) g_step_s[i] = 0; }
+}
+void zkgpu_set_trace(void (*fn)(const char*, const void*, size_t)) { g_trace = fn; }
+
+int zkgpu_pk_create(uint64_t srs, const uint8_t* circuit_blob, size_t blob_len, uint64_t* pk_out) {
+    API_BEGIN
+    Context& C = ctx(); C.require();
+    ZK_REQUIRE(circuit_blob && pk_out, "null pointer");
+    std::unique_ptr<PkEntry> pk = keygen(C, srs, circuit_blob, blob_len);
+    uint64_t h = g_next_pk++;
+    g_pks[h] = std::move(pk);
+    *pk_out = h;
+    API_END
+}
+int zkgpu_pk_release(uint64_t pk) {
+    API_BEGIN
+    ZK_REQUIRE(g_pks.erase(pk) == 1, "unknown proving key handle");
+    API_END
+}
+int zkgpu_pk_info(uint64_t pk, uint64_t info[16]) {
+    API_BEGIN
+    auto it = g_pks.find(pk);
+    ZK_REQUIRE(it != g_pks.end() && info, "unknown proving key handle");
+    const PkEntry& p = *it->second;
+    uint64_t v[16] = {p.k, p.n, p.A, p.F, p.cs.degree(), p.bf, p.P, p.Q, p.num_evals, p.proof_len, p.ek, p.S, p.plan.sets.size(), default_batch(p), 0, 0};
+    memcpy(info, v, sizeof v);
+    API_END
+}
+int zkgpu_pk_vk(uint64_t pk, uint64_t* fixed_commitments, uint64_t* perm_commitments, uint64_t digest[4]) {
+    API_BEGIN
+    auto it = g_pks.find(pk);
+    ZK_REQUIRE(it != g_pks.end(), "unknown proving key handle");
+    const PkEntry& p = *it->second;
+    if (fixed_commitments && !p.fixed_commitments.empty()) memcpy(fixed_commitments, p.fixed_commitments.data(), p.fixed_commitments.size() * 64);
+    if (perm_commitments && !p.perm_commitments.empty()) memcpy(perm_commitments, p.perm_commitments.data(), p.perm_commitments.size() * 64);
+    if (digest) memcpy(digest, p.digest.l, 32);
+    API_END
+}
+int zkgpu_prove_batch(uint64_t pk, const uint64_t* advice, const uint64_t* instance, size_t num_instance, size_t m,
+                      const uint64_t* rng_seeds, uint8_t* proofs_out, size_t proof_len) {
+    API_BEGIN
+    prove_batch(pk, advice, false, instance, num_instance, m, rng_seeds, proofs_out, proof_len);
+    API_END
+}
+int zkgpu_prove_batch_dev(uint64_t pk, const void* d_advice, const uint64_t* instance, size_t num_instance, size_t m,
+                          const uint64_t* rng_seeds, uint8_t* proofs_out, size_t proof_len) {
+    API_BEGIN
+    prove_batch(pk, reinterpret_cast<const uint64_t*>(d_advice), true, instance, num_instance, m, rng_seeds, proofs_out, proof_len);
+    API_END
+}
+
+}  // extern "C"

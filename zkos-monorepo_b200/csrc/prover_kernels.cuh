@@ -1,0 +1,91 @@
+// Device-side building blocks of the batched create_proof pipeline (prover_kernels.cu).
+// Every launcher works on a sub-batch of B independent proofs of the same circuit.
+#pragma once
+#include "common.cuh"
+#include "fp.cuh"
+
+namespace zk {
+
+struct ColSrc { uint32_t type, index; };  // COL_ADVICE / COL_FIXED / COL_INSTANCE
+
+// Per-proof Fiat-Shamir challenges (Montgomery), device resident: [B] of this struct
+struct Challenges { fr_t beta, gamma, y, x; };
+
+// dst[b*proof_stride + col*col_stride + row_start + j] = from_u512(raw[(b*cols + col)*rows + j])
+void launch_scatter_random(fr_t* dst, size_t proof_stride, size_t col_stride, size_t row_start, const uint64_t* raw_wide,
+                           size_t B, size_t cols, size_t rows, cudaStream_t st);
+
+struct PermArgs {
+    const fr_t* adv;  size_t adv_proof_stride;   // [B][A][n] Lagrange values
+    const fr_t* inst; size_t inst_proof_stride;  // [B][n]
+    const fr_t* fixed_vals;                      // [F][n]
+    const fr_t* sigma_vals;                      // [S][n]
+    const ColSrc* cols;                          // [S] permutation columns (device)
+    const fr_t* delta_pows;                      // [S] delta^c
+    const fr_t* omega_tw;                        // omega^i, i < n/2
+    const Challenges* ch;                        // [B]
+    unsigned k, S, chunk, P;
+};
+// num/den: [B][P][n]
+void launch_perm_num_den(const PermArgs& a, fr_t* num, fr_t* den, size_t B, cudaStream_t st);
+// in-place batch inversion of `count` elements (zeros stay zero)
+void launch_batch_inverse(fr_t* a, size_t count, cudaStream_t st);
+// z_local[b][s][row] = prod_{i<row} num*den_inv  (exclusive prefix product), one CTA per (b,s)
+void launch_perm_scan(const fr_t* num, const fr_t* den_inv, fr_t* z, unsigned k, size_t BP, cudaStream_t st);
+// chain the sets (z_s *= prod_{t<s} z_t[u]) and overwrite the last bf rows with blinding values
+void launch_perm_finalize(fr_t* z, unsigned k, unsigned P, unsigned bf, const uint64_t* raw_wide /*[B][P][bf] x 8 u64*/, size_t B, cudaStream_t st);
+
+// random polynomial of the vanishing argument: coefficient i of proof b = Fr::random of ChaCha20(seed_b) block i
+void launch_chacha_poly(const uint8_t* seeds /*[B][32]*/, fr_t* out /*[B][n]*/, size_t n, size_t B, cudaStream_t st);
+
+struct EvalHArgs {
+    // per-proof extended cosets
+    const fr_t* adv_ext; size_t adv_ext_proof_stride;  // [B][A+1][en], instance coset at column A
+    const fr_t* z_ext;   size_t z_ext_proof_stride;    // [B][P][en]
+    // proving key
+    const fr_t* fixed_ext;   // [F][en]
+    const fr_t* sigma_ext;   // [S][en]
+    const fr_t* l0; const fr_t* l_last; const fr_t* l_active;  // [en]
+    const fr_t* t_inv;       // [2^(ek-k)]
+    const fr_t* ext_tw;      // ext_omega^i, i < en/2
+    const fr_t* delta_pows;  // unused by the kernel (delta is a constant) — kept for symmetry
+    const ColSrc* cols;      // [S]
+    const Challenges* ch;    // [B]
+    // gate programs
+    const uint32_t* prog;        // concatenated (op,arg) pairs
+    const uint32_t* gate_off;    // [num_gates+1] offsets into prog (in instructions)
+    const fr_t* constants;
+    const int32_t* adv_q;  // [num_advice_queries][2] = (column, rotation)
+    const int32_t* fix_q;
+    const int32_t* inst_q;
+    unsigned num_gates, A, S, chunk, P, k, ek;
+    int rotation_last;
+    fr_t zeta;  // coset generator (Montgomery)
+};
+void launch_eval_h(const EvalHArgs& a, fr_t* h /*[B][en]*/, size_t B, cudaStream_t st);
+
+struct EvalJob { const fr_t* poly; fr_t x; };
+// out[j] = poly_j(x_j) for polynomials of n = 2^k coefficients
+void launch_poly_eval(const EvalJob* jobs, fr_t* out, size_t num_jobs, unsigned k, cudaStream_t st);
+
+struct LinTerm { const fr_t* poly; fr_t coef; };
+// out_j[i] = sum_{t in [off_j, off_{j+1})} coef_t * poly_t[i], i < n
+void launch_lincomb(const LinTerm* terms, const uint32_t* job_off, fr_t* const* outs, size_t num_jobs, size_t n, cudaStream_t st);
+// a_j[i] -= low_j[i] for i < cnt (low-degree correction r(X))
+void launch_sub_low(fr_t* const* polys, const fr_t* low /*[jobs][4]*/, size_t num_jobs, cudaStream_t st);
+// out_j = in_j / (X - pt_j) (remainder dropped), n coefficients in, n out (top coefficient zero)
+struct DivJob { const fr_t* in; fr_t* out; const fr_t* low; fr_t pt; };  // low: optional 4 coefficients subtracted from `in` on load
+void launch_kate_div(const DivJob* jobs, size_t num_jobs, unsigned k, cudaStream_t st);
+
+// sigma values for keygen: out[c][row] = delta^{map_col} * omega^{map_row}
+void launch_sigma_values(const uint32_t* map_col, const uint32_t* map_row, const fr_t* delta_pows, const fr_t* omega_tw, fr_t* out,
+                         size_t S, unsigned k, cudaStream_t st);
+// out[i] = 1 - a[i] - b[i]
+void launch_one_minus_sum(const fr_t* a, const fr_t* b, fr_t* out, size_t n, cudaStream_t st);
+// elementwise helpers (also exported through the C ABI for synthetic witness generation):
+// op 0 mul, 1 add, 2 sub, 3 to_mont(a), 4 from_mont(a) (b unused for 3/4)
+void launch_vec_op(int op, const fr_t* a, const fr_t* b, fr_t* out, size_t n, cudaStream_t st);
+// dst[i] = from_u512(raw[i])
+void launch_reduce_wide(const uint64_t* raw_wide, fr_t* out, size_t n, cudaStream_t st);
+
+}  // namespace zk

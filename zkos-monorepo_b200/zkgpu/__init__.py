@@ -108,6 +108,15 @@ def fft_g1(points_jacobian, omega, log_n):
     return pts
 
 
+def params_setup(k, seed):
+    """ParamsKZG::setup(k, SmallRng::seed_from_u64(seed)) -> (g, g_lagrange) as (n, 8) uint64 arrays"""
+    n = 1 << k
+    g = np.empty((n, 8), dtype=np.uint64)
+    gl = np.empty((n, 8), dtype=np.uint64)
+    _chk(lib().zkgpu_params_setup(C.c_uint32(k), C.c_uint64(seed), _p(g), _p(gl)))
+    return g, gl
+
+
 class ParamsKZG:
     """Device-resident SRS: ParamsKZG::{commit, commit_lagrange}; `Blind` is ignored by KZG."""
 
@@ -198,3 +207,77 @@ class EvaluationDomain:
 def ntt_batch_dev(d_ptr, omega, log_n, m, d_scratch_ptr=0, stream=0):
     _chk(lib().zkgpu_ntt_fr_batch_dev(C.c_void_p(d_ptr), _p(_u64(omega)), C.c_uint32(log_n), C.c_size_t(m),
                                       C.c_void_p(d_scratch_ptr), C.c_void_p(stream)))
+
+
+class ProvingKey:
+    """Device-resident halo2 ProvingKey for one circuit: keygen_vk + keygen_pk over a ParamsKZG of the
+    same k (what `generate_keys_with_min_k` returns, /root/reference/crates/shielder_bindings/build.rs:22),
+    and the batched `generate_proof` funnel
+    (/root/reference/crates/shielder_bindings/src/circuits/mod.rs:103-111)."""
+
+    INFO = ("k", "n", "num_advice", "num_fixed", "degree", "blinding_factors", "num_perm_sets", "num_quotients",
+            "num_evals", "proof_len", "extended_k", "num_perm_columns", "num_rotation_sets", "sub_batch")
+
+    def __init__(self, params, circuit_blob):
+        self.params = params
+        h = C.c_uint64(0)
+        blob = bytes(circuit_blob)
+        _chk(lib().zkgpu_pk_create(C.c_uint64(params.handle), blob, C.c_size_t(len(blob)), C.byref(h)))
+        self.handle = h.value
+        info = np.zeros(16, dtype=np.uint64)
+        _chk(lib().zkgpu_pk_info(C.c_uint64(self.handle), _p(info)))
+        for name, v in zip(self.INFO, info):
+            setattr(self, name, int(v))
+
+    def vk(self):
+        fc = np.zeros((self.num_fixed, 8), dtype=np.uint64)
+        pc = np.zeros((self.num_perm_columns, 8), dtype=np.uint64)
+        dg = np.zeros(4, dtype=np.uint64)
+        _chk(lib().zkgpu_pk_vk(C.c_uint64(self.handle), _p(fc), _p(pc), _p(dg)))
+        return fc, pc, dg
+
+    def prove_batch(self, advice, instance, seeds):
+        """advice (m, A, n, 4), instance (m, num_pi, 4), seeds (m,) -> list of m proofs (bytes)"""
+        advice, instance = _u64(advice), _u64(instance)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        m = seeds.size
+        if advice.size != m * self.num_advice * self.n * 4:
+            raise ZkGpuError("prove_batch: advice must be m x num_advice x n field elements")
+        num_pi = instance.size // (4 * m) if m else 0
+        out = np.zeros(m * self.proof_len, dtype=np.uint8)
+        _chk(lib().zkgpu_prove_batch(C.c_uint64(self.handle), _p(advice), _p(instance), C.c_size_t(num_pi), C.c_size_t(m),
+                                     _p(seeds), _p(out), C.c_size_t(self.proof_len)))
+        raw = out.tobytes()
+        return [raw[i * self.proof_len:(i + 1) * self.proof_len] for i in range(m)]
+
+    def prove_batch_dev(self, d_advice_ptr, instance, seeds, out=None):
+        """advice already resident in HBM (device pointer); returns the proofs as one uint8 array"""
+        instance = _u64(instance)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        m = seeds.size
+        num_pi = instance.size // (4 * m) if m else 0
+        if out is None:
+            out = np.zeros(m * self.proof_len, dtype=np.uint8)
+        _chk(lib().zkgpu_prove_batch_dev(C.c_uint64(self.handle), C.c_void_p(d_advice_ptr), _p(instance), C.c_size_t(num_pi),
+                                         C.c_size_t(m), _p(seeds), _p(out), C.c_size_t(self.proof_len)))
+        return out
+
+    def prove(self, advice, instance, seed):
+        """generate_proof(params, pk, circuit, public_input, rng) for one proof"""
+        return self.prove_batch(np.asarray(advice)[None], np.asarray(instance)[None], [seed])[0]
+
+    def release(self):
+        if self.handle:
+            lib().zkgpu_pk_release(C.c_uint64(self.handle))
+            self.handle = 0
+
+
+TRACE_FN = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p, C.c_size_t)
+
+
+def set_trace(fn):
+    """fn(name: bytes, data_ptr, nbytes) per prover stage of proof 0, or None to disable.  Keep the returned
+    object alive while tracing."""
+    cb = TRACE_FN(fn) if fn is not None else C.cast(None, TRACE_FN)
+    lib().zkgpu_set_trace(cb)
+    return cb
