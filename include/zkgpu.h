@@ -132,6 +132,14 @@ void zkgpu_prover_step_seconds(double out[8], int reset);
 /* test hook: called with (stage name, field elements of proof 0 of each sub-batch, byte count) */
 void zkgpu_set_trace(void (*fn)(const char* name, const void* data, size_t bytes));
 
+/* Per-kernel-class device timing (bench.py's roofline line): when enabled, CUDA events are recorded on the
+ * launching stream around every launch group of a class.  Slots: 0 MSM bucket accumulation, 1 MSM digit
+ * sort (count/scan/scatter), 2 MSM bucket reduction, 3 NTT tile passes, 4 quotient evaluation,
+ * 5 permutation products, 6 polynomial evaluation / SHPLONK algebra. */
+void zkgpu_kernel_timing(int enable);
+int zkgpu_kernel_times(int slot, double* total_ms, uint64_t* launches, int reset);
+/* the library's CUDA stream (cudaStream_t) after zkgpu_init, for event timing by the caller */
+void* zkgpu_stream(void);
 /* number of kernel launches issued by this library in this process so far */
 uint64_t zkgpu_launch_count(void);
 

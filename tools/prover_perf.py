@@ -29,7 +29,7 @@ adv = np.broadcast_to(adv1, (m,) + adv1.shape).copy()
 pi = np.broadcast_to(pi1, (m,) + pi1.shape).copy()
 seeds = np.arange(m, dtype=np.uint64) + 1
 steps = (C.c_double * 8)()
-for it in range(3):
+for it in range(int(sys.argv[3]) if len(sys.argv) > 3 else 3):
     zkgpu.lib().zkgpu_prover_step_seconds(steps, 1)
     t = time.time()
     proofs = pk.prove_batch(adv, pi, seeds)

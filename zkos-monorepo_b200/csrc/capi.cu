@@ -13,6 +13,40 @@ std::atomic<uint64_t> g_launches{0};
 Context& ctx() { static Context c; return c; }
 thread_local std::string g_last_error;
 
+// ---- per-kernel-class timing ------------------------------------------------------------------
+bool g_ktime_on = false;
+namespace {
+struct KtSlot { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending; std::vector<cudaEvent_t> free_ev; double ms = 0; uint64_t launches = 0; };
+KtSlot g_kt[KT_SLOTS];
+std::mutex g_kt_mu;
+cudaEvent_t kt_event(KtSlot& s) {
+    if (!s.free_ev.empty()) { cudaEvent_t e = s.free_ev.back(); s.free_ev.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void kt_collect(KtSlot& s) {
+    for (auto& pr : s.pending) {
+        if (cudaEventSynchronize(pr.second) == cudaSuccess) {
+            float ms = 0; if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { s.ms += ms; s.launches++; }
+        }
+        s.free_ev.push_back(pr.first); s.free_ev.push_back(pr.second);
+    }
+    s.pending.clear();
+}
+}  // namespace
+void ktime_begin(int slot, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_kt_mu);
+    KtSlot& s = g_kt[slot];
+    cudaEvent_t a = kt_event(s), b = kt_event(s);
+    cudaEventRecord(a, st);
+    s.pending.push_back({a, b});
+}
+void ktime_end(int slot, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_kt_mu);
+    KtSlot& s = g_kt[slot];
+    if (!s.pending.empty()) cudaEventRecord(s.pending.back().second, st);
+    if (s.pending.size() > 4096) kt_collect(s);
+}
+
 void Context::init(int dev) {
     std::lock_guard<std::recursive_mutex> lk(mu);
     if (inited) {
@@ -96,6 +130,18 @@ extern "C" {
 int zkgpu_abi_version(void) { return 2; }
 const char* zkgpu_last_error(void) { return g_last_error.c_str(); }
 uint64_t zkgpu_launch_count(void) { return g_launches.load(); }
+
+void zkgpu_kernel_timing(int enable) { g_ktime_on = enable != 0; }
+int zkgpu_kernel_times(int slot, double* total_ms, uint64_t* launches, int reset) {
+    if (slot < 0 || slot >= KT_SLOTS) return ZKGPU_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_kt_mu);
+    kt_collect(g_kt[slot]);
+    if (total_ms) *total_ms = g_kt[slot].ms;
+    if (launches) *launches = g_kt[slot].launches;
+    if (reset) { g_kt[slot].ms = 0; g_kt[slot].launches = 0; }
+    return ZKGPU_OK;
+}
+void* zkgpu_stream(void) { return ctx().inited ? (void*)ctx().stream : nullptr; }
 
 int zkgpu_init(int device) {
     API_BEGIN

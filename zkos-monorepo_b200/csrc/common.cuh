@@ -33,6 +33,18 @@ extern std::atomic<uint64_t> g_launches;  // kernels launched by this library (z
         ZK_CUDA(cudaGetLastError());                       \
     } while (0)
 
+// Optional per-kernel-class device timing (zkgpu_kernel_timing): CUDA events recorded on the launching stream
+// around the launches of one class; read back with zkgpu_kernel_times.  Off by default (no events recorded).
+enum { KT_MSM_BUCKETS = 0, KT_MSM_SORT = 1, KT_MSM_REDUCE = 2, KT_NTT = 3, KT_EVAL_H = 4, KT_PERM = 5, KT_POLY = 6, KT_SLOTS = 8 };
+extern bool g_ktime_on;
+void ktime_begin(int slot, cudaStream_t st);
+void ktime_end(int slot, cudaStream_t st);
+struct KtScope {
+    int slot; cudaStream_t st;
+    KtScope(int s, cudaStream_t t) : slot(s), st(t) { if (g_ktime_on) ktime_begin(slot, st); }
+    ~KtScope() { if (g_ktime_on) ktime_end(slot, st); }
+};
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;

@@ -97,22 +97,65 @@ __global__ void k_msm_scatter(const fr_t* __restrict__ scalars, size_t total, Ms
     });
 }
 
+// Buckets of one MSM ordered by decreasing run length (counting sort on the length, one CTA per MSM), so the
+// 32 lanes of a warp in k_msm_buckets walk runs of (nearly) equal length instead of idling behind the longest.
+#define ZK_HEAVY 192
+__global__ void __launch_bounds__(1024) k_msm_order(const uint32_t* __restrict__ offsets, uint32_t* __restrict__ order, unsigned K) {
+    __shared__ uint32_t hist[ZK_HEAVY + 2];
+    const uint32_t* o = offsets + (size_t)blockIdx.x * (K + 1);
+    uint32_t* ord = order + (size_t)blockIdx.x * K;
+    for (unsigned i = threadIdx.x; i < ZK_HEAVY + 2; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (unsigned key = threadIdx.x; key < K; key += blockDim.x) {
+        uint32_t sz = o[key + 1] - o[key];
+        atomicAdd(&hist[sz > ZK_HEAVY ? ZK_HEAVY + 1 : sz], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t pos = 0;
+        for (int sz = ZK_HEAVY + 1; sz >= 0; --sz) { uint32_t c = hist[sz]; hist[sz] = pos; pos += c; }
+    }
+    __syncthreads();
+    for (unsigned key = threadIdx.x; key < K; key += blockDim.x) {
+        uint32_t sz = o[key + 1] - o[key];
+        ord[atomicAdd(&hist[sz > ZK_HEAVY ? ZK_HEAVY + 1 : sz], 1u)] = key;
+    }
+}
+
+// Buckets holding more than ZK_HEAVY entries (repeated scalars: selector-like 0/1 columns, constant grand
+// products) are deferred to k_msm_heavy so that one thread never walks a long run alone.
 __global__ void __launch_bounds__(128) k_msm_buckets(const g1_affine_t* __restrict__ bases, const uint32_t* __restrict__ offsets,
                                                      const uint32_t* __restrict__ entries, MsmDims D, size_t M,
-                                                     g1_xyzz_t* __restrict__ buckets) {
+                                                     g1_xyzz_t* __restrict__ buckets, const uint32_t* __restrict__ order,
+                                                     uint32_t* __restrict__ heavy_count, uint64_t* __restrict__ heavy_list) {
     const size_t K = (size_t)D.G * D.nb;
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * K) return;
-    size_t m = idx / K, key = idx - m * K;
+    size_t m = idx / K;
+    const size_t key = order[idx];
+    idx = m * K + key;
     const uint32_t* om = offsets + m * (K + 1);
     const uint32_t* em = entries + m * ((size_t)D.n * D.W);
     uint32_t b = om[key], e = om[key + 1];
+    if (e - b > ZK_HEAVY) {
+        heavy_list[atomicAdd(heavy_count, 1u)] = idx;
+        return;
+    }
     g1_xyzz_t acc = g1_xyzz_t::identity();
-    for (uint32_t t = b; t < e; ++t) {
-        uint32_t ref = em[t];
+    if (b < e) {
+        // software pipeline: the next point is in flight while the current one is added
+        uint32_t ref = em[b];
         const g1_affine_t* p = bases + (ref & 0x7fffffffu);
         g1_affine_t q;
         q.x = fe_ldg(&p->x); q.y = fe_ldg(&p->y);
+        for (uint32_t t = b + 1; t < e; ++t) {
+            uint32_t ref_n = em[t];
+            const g1_affine_t* pn = bases + (ref_n & 0x7fffffffu);
+            g1_affine_t qn;
+            qn.x = fe_ldg(&pn->x); qn.y = fe_ldg(&pn->y);
+            xyzz_madd(acc, q, (ref >> 31) != 0);
+            q = qn; ref = ref_n;
+        }
         xyzz_madd(acc, q, (ref >> 31) != 0);
     }
     g1_xyzz_t* o = buckets + idx;
@@ -126,6 +169,39 @@ __device__ __forceinline__ g1_xyzz_t xyzz_load(const g1_xyzz_t* p) {
 }
 __device__ __forceinline__ void xyzz_store(g1_xyzz_t* p, const g1_xyzz_t& v) {
     fe_store(&p->x, v.x); fe_store(&p->y, v.y); fe_store(&p->zz, v.zz); fe_store(&p->zzz, v.zzz);
+}
+
+// One CTA per heavy bucket (grid-stride over the worklist): every thread accumulates a strided slice of the
+// run, then a shared-memory tree folds the 128 partial sums.
+__global__ void __launch_bounds__(128) k_msm_heavy(const g1_affine_t* __restrict__ bases, const uint32_t* __restrict__ offsets,
+                                                   const uint32_t* __restrict__ entries, MsmDims D, g1_xyzz_t* __restrict__ buckets,
+                                                   const uint32_t* __restrict__ heavy_count, const uint64_t* __restrict__ heavy_list) {
+    __shared__ g1_xyzz_t part[128];
+    const size_t K = (size_t)D.G * D.nb;
+    const uint32_t count = *heavy_count;
+    for (uint32_t h = blockIdx.x; h < count; h += gridDim.x) {
+        const size_t idx = heavy_list[h];
+        const size_t m = idx / K, key = idx - m * K;
+        const uint32_t* om = offsets + m * (K + 1);
+        const uint32_t* em = entries + m * ((size_t)D.n * D.W);
+        const uint32_t b = om[key], e = om[key + 1];
+        g1_xyzz_t acc = g1_xyzz_t::identity();
+        for (uint32_t t = b + threadIdx.x; t < e; t += blockDim.x) {
+            uint32_t ref = em[t];
+            const g1_affine_t* p = bases + (ref & 0x7fffffffu);
+            g1_affine_t q;
+            q.x = fe_ldg(&p->x); q.y = fe_ldg(&p->y);
+            xyzz_madd(acc, q, (ref >> 31) != 0);
+        }
+        part[threadIdx.x] = acc;
+        __syncthreads();
+        for (unsigned s = blockDim.x >> 1; s > 0; s >>= 1) {
+            if (threadIdx.x < s) part[threadIdx.x] = xyzz_add(part[threadIdx.x], part[threadIdx.x + s]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) xyzz_store(buckets + idx, part[0]);
+        __syncthreads();
+    }
 }
 
 // block per (m, g); T = blockDim.x threads, each owns L = nb/T consecutive buckets
@@ -219,6 +295,9 @@ void MsmWorkspace::ensure(const MsmPlan& p, size_t M) {
     entries.ensure(M * p.entries_per_msm());
     buckets.ensure(M * K);
     groups.ensure(M * p.G);
+    order.ensure(M * K);
+    heavy_count.ensure(1);
+    heavy_list.ensure(M * p.entries_per_msm() / ZK_HEAVY + 1);
 }
 
 static MsmDims dims_of(const MsmPlan& p) {
@@ -236,12 +315,23 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
     const size_t K = plan.K();
     const size_t total = M * plan.n;
     ZK_REQUIRE(K <= (1u << 30), "msm: too many buckets");
-    ZK_LAUNCH(k_msm_count, ceil_div(total, 256), 256, 0, st, d_scalars, total, D, ws.counts.p);
-    unsigned scan_threads = K >= 1024 ? 1024 : 32;
-    while (scan_threads < K && scan_threads < 1024) scan_threads <<= 1;
-    ZK_LAUNCH(k_msm_scan, (unsigned)M, scan_threads, 0, st, ws.counts.p, ws.offsets.p, (unsigned)K);
-    ZK_LAUNCH(k_msm_scatter, ceil_div(total, 256), 256, 0, st, d_scalars, total, D, ws.counts.p, ws.offsets.p, ws.entries.p);
-    ZK_LAUNCH(k_msm_buckets, ceil_div(M * K, 128), 128, 0, st, d_bases, ws.offsets.p, ws.entries.p, D, M, ws.buckets.p);
+    {
+        KtScope kt(KT_MSM_SORT, st);
+        ZK_LAUNCH(k_msm_count, ceil_div(total, 256), 256, 0, st, d_scalars, total, D, ws.counts.p);
+        unsigned scan_threads = K >= 1024 ? 1024 : 32;
+        while (scan_threads < K && scan_threads < 1024) scan_threads <<= 1;
+        ZK_LAUNCH(k_msm_scan, (unsigned)M, scan_threads, 0, st, ws.counts.p, ws.offsets.p, (unsigned)K);
+        ZK_LAUNCH(k_msm_scatter, ceil_div(total, 256), 256, 0, st, d_scalars, total, D, ws.counts.p, ws.offsets.p, ws.entries.p);
+        ZK_LAUNCH(k_msm_order, (unsigned)M, K >= 1024 ? 1024 : 256, 0, st, ws.offsets.p, ws.order.p, (unsigned)K);
+    }
+    {
+        KtScope kt(KT_MSM_BUCKETS, st);
+        ZK_CUDA(cudaMemsetAsync(ws.heavy_count.p, 0, sizeof(uint32_t), st));
+        ZK_LAUNCH(k_msm_buckets, ceil_div(M * K, 128), 128, 0, st, d_bases, ws.offsets.p, ws.entries.p, D, M, ws.buckets.p,
+                  ws.order.p, ws.heavy_count.p, ws.heavy_list.p);
+        ZK_LAUNCH(k_msm_heavy, 148 * 8, 128, 0, st, d_bases, ws.offsets.p, ws.entries.p, D, ws.buckets.p, ws.heavy_count.p, ws.heavy_list.p);
+    }
+    KtScope kt(KT_MSM_REDUCE, st);
     unsigned T = plan.nb < ZK_REDUCE_T ? plan.nb : ZK_REDUCE_T;
     g1_xyzz_t* groups = plan.precomp ? d_out : ws.groups.p;
     ZK_LAUNCH(k_msm_reduce, (unsigned)(M * plan.G), T, 0, st, ws.buckets.p, D, groups);

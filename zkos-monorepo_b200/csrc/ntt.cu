@@ -210,6 +210,7 @@ static void launch_pass(const NttPass& P, size_t batch, cudaStream_t st) {
     }
     size_t blocks = batch * P.tiles_per_poly;
     ZK_REQUIRE(blocks < (1ull << 31), "ntt: grid too large");
+    KtScope kt(KT_NTT, st);
     ZK_LAUNCH(k_ntt_tile, (unsigned)blocks, threads, smem, st, P);
 }
 

@@ -484,10 +484,13 @@ static void prove_sub_batch(Context& C, PkEntry& pk, const fr_t* advice, bool ad
         pa.adv = W.adv.p; pa.adv_proof_stride = A * n; pa.inst = W.inst.p; pa.inst_proof_stride = n;
         pa.fixed_vals = pk.fixed_vals.p; pa.sigma_vals = pk.sigma_vals.p; pa.cols = pk.cols.p; pa.delta_pows = pk.delta_pows.p;
         pa.omega_tw = pk.omega_tw; pa.ch = W.ch.p; pa.k = pk.k; pa.S = pk.S; pa.chunk = pk.chunk; pa.P = pk.P;
+        KtScope kt(KT_PERM, st);
         launch_perm_num_den(pa, num, den, B, st);
         launch_batch_inverse(den, B * P * n, st);
         launch_perm_scan(num, den, W.z.p, pk.k, B * P, st);
         launch_perm_finalize(W.z.p, pk.k, pk.P, pk.bf, W.raw_z.p, B, st);
+    }
+    if (P) {
         trace_dev("z", W.z.p, n, P, n, st);
         commit(C, pk, 1, W.z.p, B * P, 0, 0, W.aff.p, st);
     }

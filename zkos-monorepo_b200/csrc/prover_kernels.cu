@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(128) k_eval_h(const EvalHArgs a, fr_t* h, size
 }
 void launch_eval_h(const EvalHArgs& a, fr_t* h, size_t B, cudaStream_t st) {
     size_t total = B << a.ek;
+    KtScope kt(KT_EVAL_H, st);
     if (total) ZK_LAUNCH(k_eval_h, ceil_div(total, 128), 128, 0, st, a, h, B);
 }
 
