@@ -38,71 +38,126 @@ struct NttPass {
     int pre_coset;       // multiply input element i by cs1 (i%3==1) / cs2 (i%3==2)
     int post_coset;      // same on output index
     int has_scale;
+    int first_window_trivial;  // inputs are zero for sequence index j >= m/8: the first three stages only replicate
     fr_t scale, cs1, cs2;
 };
 
-__device__ __forceinline__ unsigned swz(unsigned p, unsigned log_m, unsigned q) {
-    // fold the top q bits (bit-reversed) into the low q bits
-    if (q == 0) return p;
-    unsigned top = p >> (log_m - q);
-    return p ^ (__brev(top) >> (32 - q));
-}
-
-__device__ __forceinline__ fr_t smem_ld(const uint32_t* s, unsigned plane, unsigned w) {
+// Shared-memory tile: two planes of uint4 (low / high 16 bytes of every element), element e of the tile at
+// plane[phys(e)].  phys XOR-folds the upper index bits into the low three, so the 8 lanes of a quarter warp
+// (one 128-byte LDS.128 / STS.128 wavefront) hit 8 different 16-byte bank groups whenever the three index
+// bits they enumerate are distinct mod 3.
+__device__ __forceinline__ unsigned phys(unsigned e) { return e ^ ((e >> 3) & 7) ^ ((e >> 6) & 7) ^ ((e >> 9) & 7); }
+__device__ __forceinline__ fr_t tile_ld(const uint4* sm, unsigned total, unsigned e) {
+    const unsigned w = phys(e);
+    uint4 a = sm[w], b = sm[total + w];
     fr_t v;
-#pragma unroll
-    for (int l = 0; l < 8; ++l) v.l[l] = s[l * plane + w];
+    v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w;
     return v;
 }
-__device__ __forceinline__ void smem_st(uint32_t* s, unsigned plane, unsigned w, const fr_t& v) {
-#pragma unroll
-    for (int l = 0; l < 8; ++l) s[l * plane + w] = v.l[l];
+__device__ __forceinline__ void tile_st(uint4* sm, unsigned total, unsigned e, const fr_t& v) {
+    const unsigned w = phys(e);
+    sm[w] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    sm[total + w] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
-__global__ void __launch_bounds__(1024, 1) k_ntt_tile(const NttPass P) {
-    extern __shared__ uint32_t smem[];
-    const unsigned log_m = P.log_m, log_C = P.log_C, q = P.swz_q;
-    const unsigned m = 1u << log_m, C = 1u << log_C, total = m << log_C;
+// One tile pass.  Radix-2 DIT stages run three at a time on 8 register-resident elements per thread (12
+// butterflies between two __syncthreads), so a 256-point column costs 3 shared-memory round trips, not 8.
+__global__ void __launch_bounds__(512) k_ntt_tile(const NttPass P) {
+    extern __shared__ uint4 sm4[];
+    const unsigned log_m = P.log_m, log_C = P.log_C;
+    const unsigned m = 1u << log_m, C = 1u << log_C, log_total = log_m + log_C, total = 1u << log_total;
     const unsigned tile = blockIdx.x % P.tiles_per_poly;
     const size_t poly = blockIdx.x / P.tiles_per_poly;
     const fr_t* in = P.in + (poly / P.in_inner) * P.in_outer_stride + (poly % P.in_inner) * P.in_poly_stride + (size_t)tile * P.in_tile_stride;
     fr_t* out = P.out + (poly / P.out_inner) * P.out_outer_stride + (poly % P.out_inner) * P.out_poly_stride + (size_t)tile * P.out_tile_stride;
 
-    for (unsigned e = threadIdx.x; e < total; e += blockDim.x) {
+    for (unsigned el = threadIdx.x; el < total; el += blockDim.x) {
         unsigned c, j;
-        if (P.c_fastest_in) { c = e & (C - 1); j = e >> log_C; } else { j = e & (m - 1); c = e >> log_m; }
+        if (P.c_fastest_in) { c = el & (C - 1); j = el >> log_C; } else { j = el & (m - 1); c = el >> log_m; }
         size_t off = (size_t)j * P.in_sj + (size_t)c * P.in_sc;
         size_t gi = (size_t)tile * P.in_tile_stride + off;  // index within the polynomial
-        fr_t v = gi < P.in_valid ? fe_load(in + off) : fr_t::zero();
-        if (P.pre_coset) {
+        const bool valid = gi < P.in_valid;
+        fr_t v = valid ? fe_load(in + off) : fr_t::zero();
+        if (P.pre_coset && valid) {
             unsigned r3 = (unsigned)(gi % 3);
             if (r3 == 1) v = v * P.cs1; else if (r3 == 2) v = v * P.cs2;
         }
-        unsigned p = swz(__brev(j) >> (32 - log_m), log_m, q);
-        smem_st(smem, total, (p << log_C) | c, v);
+        unsigned p = __brev(j) >> (32 - log_m);
+        tile_st(sm4, total, (p << log_C) | c, v);
     }
     __syncthreads();
 
-    for (unsigned s = 0; s < log_m; ++s) {
-        const unsigned half = 1u << s;
-        for (unsigned e = threadIdx.x; e < (total >> 1); e += blockDim.x) {
-            unsigned c = e & (C - 1), b = e >> log_C;
-            unsigned jj = b & (half - 1);
-            unsigned i = ((b >> s) << (s + 1)) | jj;
-            unsigned lo = (swz(i, log_m, q) << log_C) | c, hi = (swz(i + half, log_m, q) << log_C) | c;
-            fr_t a = smem_ld(smem, total, lo), bb = smem_ld(smem, total, hi);
-            if (jj) bb = bb * fe_ldg(P.tw + ((size_t)jj << (P.log_N - s - 1)));
-            smem_st(smem, total, lo, a + bb);
-            smem_st(smem, total, hi, a - bb);
+    if (log_m >= 3) {
+        const unsigned groups = total >> 3;
+        for (unsigned done = 0; done < log_m;) {
+            const unsigned s0 = done + 3 <= log_m ? done : log_m - 3;  // window [s0, s0+3); the last one may overlap
+            const unsigned st_begin = done - s0;
+            const unsigned fb = log_C + s0;                             // the window's bit field inside e
+            for (unsigned g = threadIdx.x; g < groups; g += blockDim.x) {
+                unsigned e_base;
+                if (fb >= 3 || log_total < fb + 6) e_base = ((g >> fb) << (fb + 3)) | (g & ((1u << fb) - 1));
+                else {
+                    unsigned rest = g >> 3;
+                    e_base = ((rest >> fb) << (fb + 6)) | ((g & 7) << (fb + 3)) | (rest & ((1u << fb) - 1));
+                }
+                fr_t x[8];
+                if (done == 0 && P.first_window_trivial) {
+                    // bit-reversed zero-padded input: only x[0] of each group is non-zero, and butterflies with a
+                    // zero partner copy it: after three stages all eight outputs equal x[0]
+                    x[0] = tile_ld(sm4, total, e_base);
+#pragma unroll
+                    for (unsigned b = 1; b < 8; ++b) tile_st(sm4, total, e_base | (b << fb), x[0]);
+                    continue;
+                }
+#pragma unroll
+                for (unsigned b = 0; b < 8; ++b) x[b] = tile_ld(sm4, total, e_base | (b << fb));
+                const unsigned jj0 = (e_base >> log_C) & ((1u << s0) - 1);  // position bits below the window
+#pragma unroll
+                for (unsigned st = 0; st < 3; ++st) {
+                    if (st < st_begin) continue;
+                    const unsigned s = s0 + st;
+                    const unsigned sh = P.log_N - s - 1;
+#pragma unroll
+                    for (unsigned q = 0; q < 4; ++q) {
+                        // pair: lo has bit st clear; q enumerates the other two bits
+                        const unsigned lo = ((q >> st) << (st + 1)) | (q & ((1u << st) - 1));
+                        const unsigned hi = lo | (1u << st);
+                        const unsigned jj = jj0 | ((lo & ((1u << st) - 1)) << s0);
+                        fr_t t = x[hi];
+                        if (jj) t = t * fe_ldg(P.tw + ((size_t)jj << sh));
+                        x[hi] = x[lo] - t;
+                        x[lo] = x[lo] + t;
+                    }
+                }
+#pragma unroll
+                for (unsigned b = 0; b < 8; ++b) tile_st(sm4, total, e_base | (b << fb), x[b]);
+            }
+            __syncthreads();
+            done = s0 + 3;
         }
-        __syncthreads();
+    } else {
+        // tiny transforms (m < 8): plain radix-2 stages
+        for (unsigned s = 0; s < log_m; ++s) {
+            const unsigned half = 1u << s;
+            for (unsigned el = threadIdx.x; el < (total >> 1); el += blockDim.x) {
+                unsigned c = el & (C - 1), b = el >> log_C;
+                unsigned jj = b & (half - 1);
+                unsigned i = ((b >> s) << (s + 1)) | jj;
+                unsigned lo = (i << log_C) | c, hi = ((i + half) << log_C) | c;
+                fr_t a = tile_ld(sm4, total, lo), bb = tile_ld(sm4, total, hi);
+                if (jj) bb = bb * fe_ldg(P.tw + ((size_t)jj << (P.log_N - s - 1)));
+                tile_st(sm4, total, lo, a + bb);
+                tile_st(sm4, total, hi, a - bb);
+            }
+            __syncthreads();
+        }
     }
 
     const size_t halfN = (size_t)1 << (P.log_N - 1);
-    for (unsigned e = threadIdx.x; e < total; e += blockDim.x) {
+    for (unsigned el = threadIdx.x; el < total; el += blockDim.x) {
         unsigned c, k;
-        if (P.c_fastest_out) { c = e & (C - 1); k = e >> log_C; } else { k = e & (m - 1); c = e >> log_m; }
-        fr_t v = smem_ld(smem, total, (swz(k, log_m, q) << log_C) | c);
+        if (P.c_fastest_out) { c = el & (C - 1); k = el >> log_C; } else { k = el & (m - 1); c = el >> log_m; }
+        fr_t v = tile_ld(sm4, total, (k << log_C) | c);
         if (P.post_twiddle) {
             size_t ex = ((size_t)tile * C + c) * k;
             if (ex) {
@@ -197,8 +252,9 @@ void ntt_clear_cache() {
 
 static void launch_pass(const NttPass& P, size_t batch, cudaStream_t st) {
     unsigned total = 1u << (P.log_m + P.log_C);
+    if (total < 8) total = 8;  // phys() permutes within aligned groups of 8
     size_t smem = (size_t)total * 32;
-    unsigned threads = total / 2 < 1024 ? (total / 2 < 32 ? 32 : total / 2) : 1024;
+    unsigned threads = total / 8 < 512 ? (total / 8 < 32 ? 32 : total / 8) : 512;
     static std::mutex mu; static std::map<int, size_t> cur;
     {
         std::lock_guard<std::mutex> lk(mu);
@@ -252,6 +308,7 @@ void ntt_run(const NttJob& J, cudaStream_t st) {
         P.c_fastest_in = 0; P.c_fastest_out = 0;
         P.pre_coset = J.pre_coset; P.post_coset = J.post_coset;
         P.has_scale = J.has_scale; P.scale = J.scale;
+        P.first_window_trivial = (log_N >= 3 && P.in_valid * 8 <= N) ? 1 : 0;
         launch_pass(P, J.batch, st);
         return;
     }
@@ -274,6 +331,8 @@ void ntt_run(const NttJob& J, cudaStream_t st) {
         A.c_fastest_in = 1; A.c_fastest_out = 1;
         A.post_twiddle = 1;
         A.pre_coset = J.pre_coset; A.post_coset = 0; A.has_scale = 0;
+        // column j of pass 1 holds polynomial indices c + n2*j: zero for j >= in_valid / n2
+        A.first_window_trivial = (log_n1 >= 3 && P.in_valid * 8 <= N && (P.in_valid % n2) == 0) ? 1 : 0;
         launch_pass(A, J.batch, st);
     }
     // pass 2: rows of the scratch, written transposed to out

@@ -28,6 +28,8 @@
 #include <set>
 #include <cstdlib>
 #include <chrono>
+#include <thread>
+#include <exception>
 
 namespace zk {
 
@@ -116,6 +118,10 @@ struct HostPinned {
 
 struct ProverWs {
     size_t B = 0;
+    cudaStream_t stream = nullptr;   // each worker owns a stream, an MSM workspace and the buffers below
+    MsmWorkspace msm;
+    DevBuf<fr_t> carries;
+    ~ProverWs() { if (stream) cudaStreamDestroy(stream); }
     DevBuf<fr_t> adv, inst, z, randp, adv_ext, z_ext, h, hpoly, comb, hx, lx, tmp1, tmp2, scratch, evals, low;
     DevBuf<uint64_t> raw_adv, raw_z;
     DevBuf<uint8_t> seeds;
@@ -145,7 +151,7 @@ struct PkEntry {
     const fr_t* ext_tw = nullptr;
     std::vector<g1_affine_t> fixed_commitments, perm_commitments;
     QueryPlan plan;
-    ProverWs ws;
+    ProverWs ws[2];   // ws[0] also serves keygen; ws[1] is the second pipeline worker
 };
 
 static std::map<uint64_t, std::unique_ptr<PkEntry>> g_pks;
@@ -168,8 +174,7 @@ static void host_batch_invert(std::vector<fr_t>& v) {
 static const size_t SCRATCH_ELEMS = (size_t)1 << 25;  // 1 GiB of two-pass NTT scratch
 
 // lagrange_to_coeff on `count` contiguous polynomials of 2^k values, in place
-static void intt_n(PkEntry& pk, fr_t* p, size_t count, cudaStream_t st) {
-    ProverWs& W = pk.ws;
+static void intt_n(PkEntry& pk, ProverWs& W, fr_t* p, size_t count, cudaStream_t st) {
     size_t per = pk.k > NTT_SINGLE_PASS_MAX_LOG ? std::max<size_t>(1, SCRATCH_ELEMS >> pk.k) : count;
     if (pk.k > NTT_SINGLE_PASS_MAX_LOG) W.scratch.ensure(std::min(count, per) << pk.k);
     for (size_t off = 0; off < count; off += per) {
@@ -180,8 +185,7 @@ static void intt_n(PkEntry& pk, fr_t* p, size_t count, cudaStream_t st) {
     }
 }
 // coeff_to_extended: groups x cols polynomials at in[(g*cols + c)*n] -> out[g*out_group_stride + c*en]
-static void coset_ext(PkEntry& pk, const fr_t* in, fr_t* out, size_t groups, size_t cols, size_t out_group_stride, cudaStream_t st) {
-    ProverWs& W = pk.ws;
+static void coset_ext(PkEntry& pk, ProverWs& W, const fr_t* in, fr_t* out, size_t groups, size_t cols, size_t out_group_stride, cudaStream_t st) {
     const bool two = pk.ek > NTT_SINGLE_PASS_MAX_LOG;
     size_t per = two ? std::max<size_t>(1, (SCRATCH_ELEMS >> pk.ek) / cols) : groups;
     if (two) W.scratch.ensure((std::min(groups, per) * cols) << pk.ek);
@@ -197,8 +201,7 @@ static void coset_ext(PkEntry& pk, const fr_t* in, fr_t* out, size_t groups, siz
     }
 }
 // extended_to_coeff on `count` contiguous extended polynomials, in place (no truncation: callers read the prefix)
-static void coset_intt(PkEntry& pk, fr_t* p, size_t count, cudaStream_t st) {
-    ProverWs& W = pk.ws;
+static void coset_intt(PkEntry& pk, ProverWs& W, fr_t* p, size_t count, cudaStream_t st) {
     const bool two = pk.ek > NTT_SINGLE_PASS_MAX_LOG;
     size_t per = two ? std::max<size_t>(1, SCRATCH_ELEMS >> pk.ek) : count;
     if (two) W.scratch.ensure(std::min(count, per) << pk.ek);
@@ -211,7 +214,7 @@ static void coset_intt(PkEntry& pk, fr_t* p, size_t count, cudaStream_t st) {
     }
 }
 // M commitments; MSM m reads scalars at (m / inner) * outer_stride + (m % inner) * n.  Affine out.
-static void commit(Context& C, PkEntry& pk, int basis, const fr_t* d_scalars, size_t M, size_t inner, size_t outer_stride,
+static void commit(Context& C, PkEntry& pk, ProverWs& W, int basis, const fr_t* d_scalars, size_t M, size_t inner, size_t outer_stride,
                    g1_affine_t* d_out, cudaStream_t st) {
     SrsEntry& S = C.get_srs(pk.srs_handle);
     MsmPlan plan = S.plan;
@@ -219,11 +222,11 @@ static void commit(Context& C, PkEntry& pk, int basis, const fr_t* d_scalars, si
     if (inner == 0) { inner = 1; outer_stride = pk.n; }
     plan.inner = inner; plan.outer_stride = outer_stride;
     size_t chunk = std::max<size_t>(inner, (1024 / inner) * inner);
-    pk.ws.xyzz.ensure(std::min(M, chunk));
+    W.xyzz.ensure(std::min(M, chunk));
     for (size_t off = 0; off < M; off += chunk) {
         size_t cnt = std::min(chunk, M - off);
-        msm_run(plan, d_scalars + (off / inner) * outer_stride, S.table[basis].p, cnt, pk.ws.xyzz.p, C.ws, st);
-        g1_normalize(pk.ws.xyzz.p, d_out + off, cnt, st);
+        msm_run(plan, d_scalars + (off / inner) * outer_stride, S.table[basis].p, cnt, W.xyzz.p, W.msm, st);
+        g1_normalize(W.xyzz.p, d_out + off, cnt, st);
     }
 }
 
@@ -277,17 +280,17 @@ static std::unique_ptr<PkEntry> keygen(Context& C, uint64_t srs_handle, const ui
     auto commit_cols = [&](const fr_t* d_vals, size_t count, std::vector<g1_affine_t>& out) {
         out.resize(count);
         if (!count) return;
-        pk.ws.aff.ensure(count);
-        commit(C, pk, 1, d_vals, count, 0, 0, pk.ws.aff.p, st);
-        ZK_CUDA(cudaMemcpyAsync(out.data(), pk.ws.aff.p, count * sizeof(g1_affine_t), cudaMemcpyDeviceToHost, st));
+        pk.ws[0].aff.ensure(count);
+        commit(C, pk, pk.ws[0], 1, d_vals, count, 0, 0, pk.ws[0].aff.p, st);
+        ZK_CUDA(cudaMemcpyAsync(out.data(), pk.ws[0].aff.p, count * sizeof(g1_affine_t), cudaMemcpyDeviceToHost, st));
         ZK_CUDA(cudaStreamSynchronize(st));
     };
     auto polys_and_cosets = [&](const DevBuf<fr_t>& vals, DevBuf<fr_t>& polys, DevBuf<fr_t>& ext, size_t count) {
         polys.alloc(std::max<size_t>(1, count * n)); ext.alloc(std::max<size_t>(1, count * en));
         if (!count) return;
         ZK_CUDA(cudaMemcpyAsync(polys.p, vals.p, count * n * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
-        intt_n(pk, polys.p, count, st);
-        coset_ext(pk, polys.p, ext.p, 1, count, count * en, st);
+        intt_n(pk, pk.ws[0], polys.p, count, st);
+        coset_ext(pk, pk.ws[0], polys.p, ext.p, 1, count, count * en, st);
     };
     // fixed columns
     pk.fixed_vals.alloc(std::max<size_t>(1, pk.F * n));
@@ -388,12 +391,11 @@ static size_t default_batch(const PkEntry& pk) {
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     size_t per = ((size_t)(pk.A + 1 + pk.P + 1) * pk.en + (size_t)(pk.A + 2 * pk.P + 8 + 3 * pk.plan.sets.size()) * pk.n) * sizeof(fr_t);
-    size_t B = (size_t)(free_b * 0.35) / std::max<size_t>(per, 1);
+    size_t B = (size_t)(free_b * 0.2) / std::max<size_t>(per, 1);
     return std::max<size_t>(1, std::min<size_t>(B, 128));
 }
 
-static void ensure_ws(PkEntry& pk, size_t B) {
-    ProverWs& W = pk.ws;
+static void ensure_ws(PkEntry& pk, ProverWs& W, size_t B) {
     const size_t n = pk.n, en = pk.en, ns = pk.plan.sets.size();
     W.B = std::max(W.B, B);
     W.adv.ensure(B * pk.A * n); W.inst.ensure(B * n); W.z.ensure(std::max<size_t>(1, B * pk.P * n)); W.randp.ensure(B * n);
@@ -409,14 +411,14 @@ static void ensure_ws(PkEntry& pk, size_t B) {
     ZK_REQUIRE(2 * B * pk.P * n <= B * (pk.A + 1) * en, "workspace aliasing assumption violated");
 }
 
-static void prove_sub_batch(Context& C, PkEntry& pk, const fr_t* advice, bool advice_on_device, const fr_t* instance, size_t num_pi,
+static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* advice, bool advice_on_device, const fr_t* instance, size_t num_pi,
                             size_t B, const uint64_t* seeds, uint8_t* proofs) {
-    ProverWs& W = pk.ws;
     const CsDesc& cs = pk.cs;
-    cudaStream_t st = C.stream;
+    if (!W.stream) ZK_CUDA(cudaStreamCreateWithFlags(&W.stream, cudaStreamNonBlocking));
+    cudaStream_t st = W.stream;
     const size_t n = pk.n, en = pk.en, A = pk.A, P = pk.P, Q = pk.Q, bf = pk.bf;
     const size_t ns = pk.plan.sets.size();
-    ensure_ws(pk, B);
+    ensure_ws(pk, W, B);
     const fr_t one = fe_one<FrTag>();
 
     StepTimer timer;
@@ -464,7 +466,7 @@ static void prove_sub_batch(Context& C, PkEntry& pk, const fr_t* advice, bool ad
     // ---- step 1: blind + commit advice --------------------------------------------------------
     launch_scatter_random(W.adv.p, A * n, n, pk.ustart, W.raw_adv.p, B, A, bf + 1, st);
     trace_dev("advice_blinded", W.adv.p, n, A, n, st);
-    commit(C, pk, 1, W.adv.p, B * A, 0, 0, W.aff.p, st);
+    commit(C, pk, W, 1, W.adv.p, B * A, 0, 0, W.aff.p, st);
     {
         const g1_affine_t* pts = fetch_points(B * A);
         for (size_t b = 0; b < B; ++b) {
@@ -488,28 +490,29 @@ static void prove_sub_batch(Context& C, PkEntry& pk, const fr_t* advice, bool ad
         launch_perm_num_den(pa, num, den, B, st);
         launch_batch_inverse(den, B * P * n, st);
         launch_perm_scan(num, den, W.z.p, pk.k, B * P, st);
-        launch_perm_finalize(W.z.p, pk.k, pk.P, pk.bf, W.raw_z.p, B, st);
+        W.carries.ensure(B * P);
+        launch_perm_finalize(W.z.p, W.carries.p, pk.k, pk.P, pk.bf, W.raw_z.p, B, st);
     }
     if (P) {
         trace_dev("z", W.z.p, n, P, n, st);
-        commit(C, pk, 1, W.z.p, B * P, 0, 0, W.aff.p, st);
+        commit(C, pk, W, 1, W.z.p, B * P, 0, 0, W.aff.p, st);
     }
     launch_chacha_poly(W.seeds.p, W.randp.p, n, B, st);
     trace_dev("random_poly", W.randp.p, n, 1, n, st);
-    commit(C, pk, 0, W.randp.p, B, 0, 0, W.aff.p + B * P, st);
+    commit(C, pk, W, 0, W.randp.p, B, 0, 0, W.aff.p + B * P, st);
     ZK_CUDA(cudaMemcpyAsync(W.h_aff.p, W.aff.p, B * (P + 1) * sizeof(g1_affine_t), cudaMemcpyDeviceToHost, st));
     cudaEvent_t ev_pts;
     ZK_CUDA(cudaEventCreateWithFlags(&ev_pts, cudaEventDisableTiming));
     ZK_CUDA(cudaEventRecord(ev_pts, st));
     // queue the transforms that do not depend on y behind the commitments
     if (P) {
-        intt_n(pk, W.z.p, B * P, st);
-        coset_ext(pk, W.z.p, W.z_ext.p, B, P, P * en, st);
+        intt_n(pk, W, W.z.p, B * P, st);
+        coset_ext(pk, W, W.z.p, W.z_ext.p, B, P, P * en, st);
     }
-    intt_n(pk, W.adv.p, B * A, st);
-    intt_n(pk, W.inst.p, B, st);
-    coset_ext(pk, W.adv.p, W.adv_ext.p, B, A, (A + 1) * en, st);
-    coset_ext(pk, W.inst.p, W.adv_ext.p + A * en, B, 1, (A + 1) * en, st);
+    intt_n(pk, W, W.adv.p, B * A, st);
+    intt_n(pk, W, W.inst.p, B, st);
+    coset_ext(pk, W, W.adv.p, W.adv_ext.p, B, A, (A + 1) * en, st);
+    coset_ext(pk, W, W.inst.p, W.adv_ext.p + A * en, B, 1, (A + 1) * en, st);
     ZK_CUDA(cudaEventSynchronize(ev_pts));
     ZK_CUDA(cudaEventDestroy(ev_pts));
     {
@@ -541,9 +544,9 @@ static void prove_sub_batch(Context& C, PkEntry& pk, const fr_t* advice, bool ad
         launch_eval_h(ea, W.h.p, B, st);
     }
     trace_dev("h_evals", W.h.p, en, 1, en, st);
-    coset_intt(pk, W.h.p, B, st);
+    coset_intt(pk, W, W.h.p, B, st);
     trace_dev("h_coeffs", W.h.p, Q * n, 1, en, st);
-    commit(C, pk, 0, W.h.p, B * Q, Q, en, W.aff.p, st);
+    commit(C, pk, W, 0, W.h.p, B * Q, Q, en, W.aff.p, st);
     {
         const g1_affine_t* pts = fetch_points(B * Q);
         for (size_t b = 0; b < B; ++b) {
@@ -717,7 +720,7 @@ static void prove_sub_batch(Context& C, PkEntry& pk, const fr_t* advice, bool ad
         upload(W.terms2, t2, st); upload(W.job_off2, off2, st); upload(W.outs2, outs2, st);
         launch_lincomb(W.terms2.p, W.job_off2.p, W.outs2.p, B, n, st);
         trace_dev("hx", W.hx.p, n, 1, n, st);
-        commit(C, pk, 0, W.hx.p, B, 0, 0, W.aff.p, st);
+        commit(C, pk, W, 0, W.hx.p, B, 0, 0, W.aff.p, st);
         const g1_affine_t* pts = fetch_points(B);
         for (size_t b = 0; b < B; ++b) { ps[b].tr.write_point(pts[b]); ps[b].mu = ps[b].tr.squeeze(); }
     }
@@ -763,7 +766,7 @@ static void prove_sub_batch(Context& C, PkEntry& pk, const fr_t* advice, bool ad
         h2d(W.div_jobs.p, divs, st);
         launch_kate_div(W.div_jobs.p, B, pk.k, st);
         trace_dev("wq", W.tmp1.p, n, 1, n, st);
-        commit(C, pk, 0, W.tmp1.p, B, 0, 0, W.aff.p, st);
+        commit(C, pk, W, 0, W.tmp1.p, B, 0, 0, W.aff.p, st);
         const g1_affine_t* pts = fetch_points(B);
         for (size_t b = 0; b < B; ++b) {
             ps[b].tr.write_point(pts[b]);
@@ -784,11 +787,29 @@ static void prove_batch(uint64_t handle, const uint64_t* advice, bool advice_on_
     ZK_REQUIRE(num_pi == 0 || instance, "null pointer");
     ZK_REQUIRE(num_pi <= pk.ustart, "prove: InstanceTooLarge");
     size_t Bmax = default_batch(pk);
-    for (size_t off = 0; off < m; off += Bmax) {
-        size_t B = std::min(Bmax, m - off);
-        prove_sub_batch(C, pk, reinterpret_cast<const fr_t*>(advice) + off * pk.A * pk.n, advice_on_device,
-                        reinterpret_cast<const fr_t*>(instance) + off * num_pi, num_pi, B, seeds + off, proofs + off * proof_len);
-    }
+    // Two pipeline workers (host thread + stream + workspace each) take alternate sub-batches, so one worker's
+    // transcript hashing and bookkeeping overlap the other's kernels.  Kernel-class timing and stage tracing
+    // use a single worker (per-kernel durations are only meaningful when launches do not share the GPU).
+    size_t nsub = (m + Bmax - 1) / Bmax;
+    unsigned workers = (nsub >= 2 && !g_ktime_on && !g_trace) ? 2 : 1;
+    if (const char* e = getenv("ZKGPU_PROVER_WORKERS")) { if (atoi(e) == 1) workers = 1; }
+    if (workers == 2 && Bmax > 1) { Bmax = std::max<size_t>(1, std::min(Bmax, (m + 3) / 4)); nsub = (m + Bmax - 1) / Bmax; }
+    const fr_t* adv = reinterpret_cast<const fr_t*>(advice);
+    const fr_t* inst = reinterpret_cast<const fr_t*>(instance);
+    auto run = [&](unsigned w) {
+        ZK_CUDA(cudaSetDevice(C.device));
+        for (size_t sb = w; sb < nsub; sb += workers) {
+            size_t off = sb * Bmax, B = std::min(Bmax, m - off);
+            prove_sub_batch(C, pk, pk.ws[w], adv + off * pk.A * pk.n, advice_on_device, inst + off * num_pi, num_pi, B, seeds + off,
+                            proofs + off * proof_len);
+        }
+    };
+    if (workers == 1) { run(0); return; }
+    std::exception_ptr err[2];
+    std::thread th[2];
+    for (unsigned w = 0; w < 2; ++w) th[w] = std::thread([&, w] { try { run(w); } catch (...) { err[w] = std::current_exception(); } });
+    for (auto& t : th) t.join();
+    for (auto& e : err) if (e) std::rethrow_exception(e);
 }
 
 }  // namespace zk

@@ -191,13 +191,11 @@ __global__ void k_perm_finalize(fr_t* z, const fr_t* carries, unsigned k, unsign
         fe_store(z + t, fe_load(z + t) * fe_load(carries + bs));
     }
 }
-void launch_perm_finalize(fr_t* z, unsigned k, unsigned P, unsigned bf, const uint64_t* raw, size_t B, cudaStream_t st) {
+void launch_perm_finalize(fr_t* z, fr_t* carries, unsigned k, unsigned P, unsigned bf, const uint64_t* raw, size_t B, cudaStream_t st) {
     if (!B || !P) return;
-    static thread_local DevBuf<fr_t> carries;
-    carries.ensure(B * P);
-    ZK_LAUNCH(k_perm_carries, ceil_div(B, 64), 64, 0, st, z, carries.p, k, P, bf, B);
+    ZK_LAUNCH(k_perm_carries, ceil_div(B, 64), 64, 0, st, z, carries, k, P, bf, B);
     size_t total = B * P << k;
-    ZK_LAUNCH(k_perm_finalize, ceil_div(total, 256), 256, 0, st, z, carries.p, k, P, bf, raw, B);
+    ZK_LAUNCH(k_perm_finalize, ceil_div(total, 256), 256, 0, st, z, carries, k, P, bf, raw, B);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -237,9 +235,11 @@ void launch_chacha_poly(const uint8_t* seeds, fr_t* out, size_t n, size_t B, cud
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_eval_h(const EvalHArgs a, fr_t* h, size_t B) {
     const size_t en = (size_t)1 << a.ek;
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= B * en) return;
-    const size_t i = t & (en - 1), b = t >> a.ek;
+    // blocks of one row range are adjacent across the B proofs, so the proving-key columns they share stay in L2
+    const size_t b = blockIdx.x % B;
+    const size_t i = (size_t)(blockIdx.x / B) * blockDim.x + threadIdx.x;
+    if (i >= en) return;
+    const size_t t = b * en + i;
     const unsigned rs = a.ek - a.k;  // rotation scale shift
     const fr_t* adv = a.adv_ext + b * a.adv_ext_proof_stride;
     const fr_t y = fe_ldg(&a.ch[b].y);
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(128) k_eval_h(const EvalHArgs a, fr_t* h, size
 void launch_eval_h(const EvalHArgs& a, fr_t* h, size_t B, cudaStream_t st) {
     size_t total = B << a.ek;
     KtScope kt(KT_EVAL_H, st);
-    if (total) ZK_LAUNCH(k_eval_h, ceil_div(total, 128), 128, 0, st, a, h, B);
+    if (total) ZK_LAUNCH(k_eval_h, (unsigned)(ceil_div((size_t)1 << a.ek, 128) * B), 128, 0, st, a, h, B);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -33,7 +33,7 @@ void launch_batch_inverse(fr_t* a, size_t count, cudaStream_t st);
 // z_local[b][s][row] = prod_{i<row} num*den_inv  (exclusive prefix product), one CTA per (b,s)
 void launch_perm_scan(const fr_t* num, const fr_t* den_inv, fr_t* z, unsigned k, size_t BP, cudaStream_t st);
 // chain the sets (z_s *= prod_{t<s} z_t[u]) and overwrite the last bf rows with blinding values
-void launch_perm_finalize(fr_t* z, unsigned k, unsigned P, unsigned bf, const uint64_t* raw_wide /*[B][P][bf] x 8 u64*/, size_t B, cudaStream_t st);
+void launch_perm_finalize(fr_t* z, fr_t* carries /*[B][P] scratch*/, unsigned k, unsigned P, unsigned bf, const uint64_t* raw_wide /*[B][P][bf] x 8 u64*/, size_t B, cudaStream_t st);
 
 // random polynomial of the vanishing argument: coefficient i of proof b = Fr::random of ChaCha20(seed_b) block i
 void launch_chacha_poly(const uint8_t* seeds /*[B][32]*/, fr_t* out /*[B][n]*/, size_t n, size_t B, cudaStream_t st);
