@@ -84,6 +84,12 @@ int zkgpu_g_to_lagrange(const uint64_t* g_affine, uint32_t k, uint64_t* out_affi
  * (/root/reference/crates/halo2-verifier/src/generator.rs:118-119): g[i] = G * s^i, g_lagrange = g_to_lagrange(g). */
 int zkgpu_params_setup(uint32_t k, uint64_t seed, uint64_t* g_out, uint64_t* g_lagrange_out);
 
+/* g_lagrange_out may be NULL (then k up to 24: bases for the large-MSM sweep). */
+
+/* Host-side sum of n affine points: the combine step of a point-sharded MSM (one partial result per GPU,
+ * gathered by the caller).  Needs no GPU. */
+int zkgpu_g1_sum_affine(const uint64_t* points_affine, size_t n, uint64_t out_affine[8]);
+
 /* ---- vectorised Fr helpers (halo2curves `Fr` ops / `Fr::random`), used to build synthetic circuits and
  * witnesses in bench.py without the CPU oracle.  op: 0 mul, 1 add, 2 sub, 3 to Montgomery, 4 from Montgomery. */
 int zkgpu_fr_vec_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);

@@ -39,7 +39,7 @@ __host__ __device__ __forceinline__ void for_each_digit(const uint32_t* s, unsig
     }
 }
 
-struct MsmDims { unsigned c, W, G, nb; unsigned precomp; unsigned n; unsigned tstride; size_t inner, outer_stride; };  // tstride: table stride (points per window)
+struct MsmDims { unsigned c, W, G, nb; unsigned precomp; unsigned n; unsigned tstride; unsigned heavy; size_t inner, outer_stride; };  // heavy: runs longer than this go to k_msm_heavy  // tstride: table stride (points per window)
 
 __global__ void k_msm_count(const fr_t* __restrict__ scalars, size_t total, MsmDims D, uint32_t* __restrict__ counts) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -99,9 +99,10 @@ __global__ void k_msm_scatter(const fr_t* __restrict__ scalars, size_t total, Ms
 
 // Buckets of one MSM ordered by decreasing run length (counting sort on the length, one CTA per MSM), so the
 // 32 lanes of a warp in k_msm_buckets walk runs of (nearly) equal length instead of idling behind the longest.
-#define ZK_HEAVY 192
-__global__ void __launch_bounds__(1024) k_msm_order(const uint32_t* __restrict__ offsets, uint32_t* __restrict__ order, unsigned K) {
-    __shared__ uint32_t hist[ZK_HEAVY + 2];
+#define ZK_HEAVY_MIN 192
+#define ZK_HEAVY_MAX 8190
+__global__ void __launch_bounds__(1024) k_msm_order(const uint32_t* __restrict__ offsets, uint32_t* __restrict__ order, unsigned K, unsigned ZK_HEAVY) {
+    extern __shared__ uint32_t hist[];  // ZK_HEAVY + 2 bins
     const uint32_t* o = offsets + (size_t)blockIdx.x * (K + 1);
     uint32_t* ord = order + (size_t)blockIdx.x * K;
     for (unsigned i = threadIdx.x; i < ZK_HEAVY + 2; i += blockDim.x) hist[i] = 0;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(1024) k_msm_order(const uint32_t* __restrict__
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t pos = 0;
-        for (int sz = ZK_HEAVY + 1; sz >= 0; --sz) { uint32_t c = hist[sz]; hist[sz] = pos; pos += c; }
+        for (int sz = (int)ZK_HEAVY + 1; sz >= 0; --sz) { uint32_t c = hist[sz]; hist[sz] = pos; pos += c; }
     }
     __syncthreads();
     for (unsigned key = threadIdx.x; key < K; key += blockDim.x) {
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(128) k_msm_buckets(const g1_affine_t* __restri
     const uint32_t* om = offsets + m * (K + 1);
     const uint32_t* em = entries + m * ((size_t)D.n * D.W);
     uint32_t b = om[key], e = om[key + 1];
-    if (e - b > ZK_HEAVY) {
+    if (e - b > D.heavy) {
         heavy_list[atomicAdd(heavy_count, 1u)] = idx;
         return;
     }
@@ -297,12 +298,16 @@ void MsmWorkspace::ensure(const MsmPlan& p, size_t M) {
     groups.ensure(M * p.G);
     order.ensure(M * K);
     heavy_count.ensure(1);
-    heavy_list.ensure(M * p.entries_per_msm() / ZK_HEAVY + 1);
+    heavy_list.ensure(M * p.entries_per_msm() / ZK_HEAVY_MIN + 1);
 }
 
 static MsmDims dims_of(const MsmPlan& p) {
     MsmDims D; D.c = p.c; D.W = p.W; D.G = p.G; D.nb = p.nb; D.precomp = p.precomp ? 1 : 0; D.n = (unsigned)p.n; D.tstride = (unsigned)(p.tstride ? p.tstride : p.n);
     D.inner = p.inner ? p.inner : ~(size_t)0; D.outer_stride = p.outer_stride;
+    // a run is "heavy" when it is several times the mean run length (and at least ZK_HEAVY_MIN)
+    size_t mean = p.entries_per_msm() / (p.K() ? p.K() : 1);
+    size_t heavy = 4 * mean < ZK_HEAVY_MIN ? ZK_HEAVY_MIN : 4 * mean;
+    D.heavy = (unsigned)(heavy > ZK_HEAVY_MAX ? ZK_HEAVY_MAX : heavy);
     return D;
 }
 
@@ -322,7 +327,7 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
         while (scan_threads < K && scan_threads < 1024) scan_threads <<= 1;
         ZK_LAUNCH(k_msm_scan, (unsigned)M, scan_threads, 0, st, ws.counts.p, ws.offsets.p, (unsigned)K);
         ZK_LAUNCH(k_msm_scatter, ceil_div(total, 256), 256, 0, st, d_scalars, total, D, ws.counts.p, ws.offsets.p, ws.entries.p);
-        ZK_LAUNCH(k_msm_order, (unsigned)M, K >= 1024 ? 1024 : 256, 0, st, ws.offsets.p, ws.order.p, (unsigned)K);
+        ZK_LAUNCH(k_msm_order, (unsigned)M, K >= 1024 ? 1024 : 256, (D.heavy + 2) * sizeof(uint32_t), st, ws.offsets.p, ws.order.p, (unsigned)K, D.heavy);
     }
     {
         KtScope kt(KT_MSM_BUCKETS, st);

@@ -26,8 +26,8 @@ extern "C" int zkgpu_params_setup(uint32_t k, uint64_t seed, uint64_t* g_out, ui
     try {
         std::lock_guard<std::recursive_mutex> lk(ctx().mu);
         Context& C = ctx(); C.require();
-        ZK_REQUIRE(g_out && g_lagrange_out, "null pointer");
-        ZK_REQUIRE(k >= 1 && k <= 20, "params_setup: k out of range");
+        ZK_REQUIRE(g_out, "null pointer");
+        ZK_REQUIRE(k >= 1 && k <= 24 && (k <= 20 || !g_lagrange_out), "params_setup: k out of range (g_lagrange up to 2^20)");
         const size_t n = (size_t)1 << k;
         cudaStream_t st = C.stream;
         // s = Fr::random(rng) = from_u512 of eight next_u64
@@ -53,6 +53,7 @@ extern "C" int zkgpu_params_setup(uint32_t k, uint64_t seed, uint64_t* g_out, ui
         ZK_LAUNCH(k_fixed_base_mul, ceil_div(n, 64), 64, 0, st, C.fr_buf.p, G, C.xyzz_buf.p, n);
         g1_normalize(C.xyzz_buf.p, C.pt_buf.p, n, st);
         ZK_CUDA(cudaMemcpyAsync(g_out, C.pt_buf.p, n * 64, cudaMemcpyDeviceToHost, st));
+        if (!g_lagrange_out) { ZK_CUDA(cudaStreamSynchronize(st)); return ZKGPU_OK; }
         // g_lagrange = n^-1 * FFT_{omega^-1}(g)
         g1_from_affine(C.pt_buf.p, C.xyzz_buf.p, n, st);
         g1_fft(C.xyzz_buf.p, k, fr_omega_inv(k), st);
@@ -60,6 +61,24 @@ extern "C" int zkgpu_params_setup(uint32_t k, uint64_t seed, uint64_t* g_out, ui
         g1_normalize(C.xyzz_buf.p, C.aff_buf.p, n, st);
         ZK_CUDA(cudaMemcpyAsync(g_lagrange_out, C.aff_buf.p, n * 64, cudaMemcpyDeviceToHost, st));
         ZK_CUDA(cudaStreamSynchronize(st));
+        return ZKGPU_OK;
+    } catch (const zk::Error& e) { g_last_error = e.what(); return e.code; }
+    catch (const std::exception& e) { g_last_error = e.what(); return ZKGPU_ERR_INTERNAL; }
+}
+
+// Sum of n affine points on the HOST (no GPU needed): the combine step of a point-sharded MSM, where every GPU
+// contributes one partial result (gather of <= 8 points, then G-1 additions).
+extern "C" int zkgpu_g1_sum_affine(const uint64_t* points_affine, size_t n, uint64_t out_affine[8]) {
+    try {
+        ZK_REQUIRE((points_affine || n == 0) && out_affine, "null pointer");
+        g1_xyzz_t acc = g1_xyzz_t::identity();
+        for (size_t i = 0; i < n; ++i) {
+            g1_affine_t p;
+            memcpy(&p, points_affine + 8 * i, 64);
+            xyzz_madd(acc, p, false);
+        }
+        g1_affine_t r = xyzz_to_affine(acc);
+        memcpy(out_affine, &r, 64);
         return ZKGPU_OK;
     } catch (const zk::Error& e) { g_last_error = e.what(); return e.code; }
     catch (const std::exception& e) { g_last_error = e.what(); return ZKGPU_ERR_INTERNAL; }

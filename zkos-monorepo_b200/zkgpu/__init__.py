@@ -108,13 +108,22 @@ def fft_g1(points_jacobian, omega, log_n):
     return pts
 
 
-def params_setup(k, seed):
-    """ParamsKZG::setup(k, SmallRng::seed_from_u64(seed)) -> (g, g_lagrange) as (n, 8) uint64 arrays"""
+def params_setup(k, seed, lagrange=True):
+    """ParamsKZG::setup(k, SmallRng::seed_from_u64(seed)) -> (g, g_lagrange) as (n, 8) uint64 arrays
+    (g_lagrange is None with lagrange=False, which allows k up to 24)"""
     n = 1 << k
     g = np.empty((n, 8), dtype=np.uint64)
-    gl = np.empty((n, 8), dtype=np.uint64)
-    _chk(lib().zkgpu_params_setup(C.c_uint32(k), C.c_uint64(seed), _p(g), _p(gl)))
+    gl = np.empty((n, 8), dtype=np.uint64) if lagrange else None
+    _chk(lib().zkgpu_params_setup(C.c_uint32(k), C.c_uint64(seed), _p(g), _p(gl) if lagrange else None))
     return g, gl
+
+
+def g1_sum(points):
+    """host-side sum of affine points (n, 8) -> (8,)"""
+    points = _u64(points)
+    out = np.zeros(8, dtype=np.uint64)
+    _chk(lib().zkgpu_g1_sum_affine(_p(points), C.c_size_t(points.size // 8), _p(out)))
+    return out
 
 
 class ParamsKZG:
