@@ -1,0 +1,40 @@
+// Host build (g++, no nvcc, no GPU) of the product's host-side prover logic — csrc/host_util.hpp (Keccak-256,
+// EVM transcript, SmallRng, byte codecs), csrc/plonk_types.hpp (constraint-system parsing, derived sizes,
+// permutation assembly) and the host paths of fp.cuh / ec.cuh.  Test-only shim exporting a small C ABI.
+#include <cstring>
+#include "host_util.hpp"
+#include "plonk_types.hpp"
+using namespace zk;
+extern "C" {
+void hl_keccak256(const uint8_t* in, size_t len, uint8_t* out) { keccak256(in, len, out); }
+void hl_smallrng(uint64_t seed, uint64_t* out, size_t n) { SmallRng r(seed); for (size_t i = 0; i < n; ++i) out[i] = r.next_u64(); }
+// transcript: absorb `n_scalars` Montgomery scalars after the digest, then squeeze `n_ch` challenges (Montgomery out)
+void hl_transcript(const uint32_t* digest, const uint32_t* scalars, size_t n_scalars, const uint32_t* points, size_t n_points,
+                   uint32_t* challenges, size_t n_ch, uint8_t* proof_out) {
+    Transcript tr(proof_out);
+    fr_t d; memcpy(d.l, digest, 32); tr.common_scalar(d);
+    for (size_t i = 0; i < n_scalars; ++i) { fr_t s; memcpy(s.l, scalars + 8 * i, 32); tr.write_scalar(s); }
+    for (size_t i = 0; i < n_points; ++i) { g1_affine_t p; memcpy(&p, points + 16 * i, 64); tr.write_point(p); }
+    for (size_t i = 0; i < n_ch; ++i) { fr_t c = tr.squeeze(); memcpy(challenges + 8 * i, c.l, 32); }
+}
+void hl_fr_from_be_reduce(const uint8_t* in, uint32_t* out) { fr_t v = fr_from_be_bytes_reduce(in); memcpy(out, v.l, 32); }
+// info = k, n, degree, blinding_factors, chunk_len, num_perm_sets, num_quotients, extended_k, num_evals, proof_len; returns 0 / -1
+int hl_cs_info(const uint8_t* blob, size_t len, uint64_t* info, char* err, size_t errlen) {
+    try {
+        CsDesc c = CsDesc::parse(blob, len);
+        uint64_t v[10] = {c.k, c.n(), c.degree(), c.blinding_factors(), c.chunk_len(), c.num_perm_sets(), c.num_quotients(), c.extended_k(), c.num_evals(), c.proof_len()};
+        memcpy(info, v, sizeof v);
+        return 0;
+    } catch (const std::exception& e) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; return -1; }
+}
+// sigma mapping after applying the blob's copy constraints: out_col/out_row [S*n]
+int hl_perm_mapping(const uint8_t* blob, size_t len, uint32_t* out_col, uint32_t* out_row) {
+    try {
+        CsDesc c = CsDesc::parse(blob, len);
+        PermAssembly as(c.perm_columns.size(), c.n());
+        for (auto& cp : c.copies) as.copy(cp.lcol, cp.lrow, cp.rcol, cp.rrow);
+        memcpy(out_col, as.map_col.data(), as.map_col.size() * 4); memcpy(out_row, as.map_row.data(), as.map_row.size() * 4);
+        return 0;
+    } catch (...) { return -1; }
+}
+}

@@ -1,0 +1,140 @@
+"""The product's host-side prover logic, built with g++ and run on the CPU (no GPU, no nvcc):
+Keccak-256 / EVM transcript / SmallRng / codecs (csrc/host_util.hpp) and the constraint-system parser,
+derived sizes and permutation assembly (csrc/plonk_types.hpp).  Pinned by the reference's own known answers
+(/root/reference/crates/shielder-account/src/secrets.rs:75-106) and cross-checked with the oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import pyref as P
+from zkgpu import circuits
+
+ROOT = O.ROOT
+CSRC = os.path.join(ROOT, "zkos-monorepo_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def hl(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("hl") / "libhostlogic.so")
+    cuda_inc = "/usr/local/cuda/include"
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-I", cuda_inc, "-I", CSRC,
+                           os.path.join(ROOT, "tests", "emu", "host_logic.cpp"), "-o", so])
+    return C.CDLL(so)
+
+
+def _keccak(hl, data):
+    out = C.create_string_buffer(32)
+    hl.hl_keccak256(data, C.c_size_t(len(data)), out)
+    return out.raw
+
+
+def test_keccak_known_answers(hl):
+    m1 = (15).to_bytes(32, "big") + b"nullifier" + (0xFF).to_bytes(4, "big")
+    assert _keccak(hl, m1).hex() == "375a07a9503d15a291307e33ad0c297c9768fea4712947172ad09f2df34d8015"
+    m2 = (16).to_bytes(32, "big") + b"id" + (26).to_bytes(8, "big") + (45).to_bytes(4, "big")
+    assert _keccak(hl, m2).hex() == "f4b3b097dfb3da737872bdf8b59a3b3723345dc147a0b8229608db69cfef6499"
+    assert _keccak(hl, b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    rng = np.random.default_rng(1)
+    for n in (1, 31, 32, 135, 136, 137, 271, 272, 273, 5000):
+        d = rng.bytes(n)
+        assert _keccak(hl, d) == O.keccak256(d), n
+
+
+def test_smallrng_matches_oracle(hl):
+    for seed in (0, 42, 2**64 - 1):
+        out = np.empty(64, dtype=np.uint64)
+        hl.hl_smallrng(C.c_uint64(seed), out.ctypes.data_as(C.c_void_p), C.c_size_t(64))
+        assert np.array_equal(out, O.smallrng(seed, 64))
+
+
+def test_challenge_reduction(hl):
+    """hash (any 256-bit value) -> Fr: values >= r, the largest word, and random ones"""
+    rng = np.random.default_rng(3)
+    vals = [0, 1, P.R_MOD - 1, P.R_MOD, P.R_MOD + 1, 5 * P.R_MOD + 7, (1 << 256) - 1] + [int.from_bytes(rng.bytes(32), "big") for _ in range(200)]
+    for v in vals:
+        out = np.empty(8, dtype=np.uint32)
+        hl.hl_fr_from_be_reduce(v.to_bytes(32, "big"), out.ctypes.data_as(C.c_void_p))
+        got = P.limbs_to_int(out.view(np.uint64))[0]
+        assert got == (v % P.R_MOD) * P.MONT_R % P.R_MOD, hex(v)
+
+
+def test_transcript_matches_spec(hl):
+    """Halo2Verifier.sol:101-124: challenge = keccak(state ‖ absorbed) mod r; a squeeze right after a squeeze
+    hashes prev_hash ‖ 0x01.  Points / scalars are written as canonical big-endian words."""
+    raw = O.srs_read(O.RAW11, 0)
+    digest = O.random_fr(9, 1)[0]
+    scalars = O.random_fr(10, 5)
+    points = raw["g"][3:6]
+    n_ch = 4
+    ch = np.empty((n_ch, 4), dtype=np.uint64)
+    proof = C.create_string_buffer(32 * 5 + 64 * 3)
+    hl.hl_transcript(digest.ctypes.data_as(C.c_void_p), scalars.ctypes.data_as(C.c_void_p), C.c_size_t(5),
+                     np.ascontiguousarray(points).ctypes.data_as(C.c_void_p), C.c_size_t(3), ch.ctypes.data_as(C.c_void_p), C.c_size_t(n_ch), proof)
+    be = lambda field, m: b"".join(int(v).to_bytes(32, "big") for v in P.limbs_to_int(O.from_mont(field, m)))
+    body = be(0, scalars) + be(1, points.reshape(-1, 4))
+    assert proof.raw == body
+    buf = be(0, digest[None]) + body
+    want = []
+    h = O.keccak256(buf); want.append(int.from_bytes(h, "big") % P.R_MOD)
+    for _ in range(n_ch - 1):
+        h = O.keccak256(h + b"\x01"); want.append(int.from_bytes(h, "big") % P.R_MOD)
+    assert P.limbs_to_int(O.from_mont(0, ch)) == want
+
+
+@pytest.mark.parametrize("name", sorted(circuits.SHAPES))
+def test_constraint_system_sizes(hl, name):
+    shape = circuits.Shape(name) if circuits.SHAPES[name]["k"] <= 9 else circuits.Shape(name, k=9)
+    circ = circuits.Circuit(shape, O.OracleBackend, seed=1)
+    info = np.zeros(10, dtype=np.uint64)
+    err = C.create_string_buffer(256)
+    assert hl.hl_cs_info(circ.blob, C.c_size_t(len(circ.blob)), info.ctypes.data_as(C.c_void_p), err, C.c_size_t(256)) == 0, err.value
+    want = [shape.k, shape.n, shape.degree, shape.blinding_factors, shape.chunk_len, shape.num_perm_sets, shape.num_quotients,
+            shape.extended_k, shape.num_evals, shape.proof_len]
+    assert [int(x) for x in info] == want
+    # proof length formula of the verifier generator (codegen/util.rs:175-186)
+    assert shape.proof_len == 64 * (shape.num_advice + shape.num_perm_sets + 1 + shape.num_quotients) + 32 * shape.num_evals + 128
+
+
+def test_malformed_blobs_rejected(hl):
+    shape = circuits.Shape("tiny")
+    blob = circuits.Circuit(shape, O.OracleBackend, seed=1).blob
+    info = np.zeros(10, dtype=np.uint64)
+    err = C.create_string_buffer(256)
+    call = lambda b: hl.hl_cs_info(bytes(b), C.c_size_t(len(b)), info.ctypes.data_as(C.c_void_p), err, C.c_size_t(256))
+    assert call(blob) == 0
+    assert call(blob[:-1]) == -1 and call(blob + b"\0") == -1 and call(b"") == -1
+    bad = bytearray(blob); bad[0] ^= 1
+    assert call(bad) == -1 and b"magic" in err.value
+    bad = bytearray(blob); bad[4:8] = (40).to_bytes(4, "little")     # k out of range
+    assert call(bad) == -1
+
+
+def test_permutation_assembly(hl):
+    shape = circuits.Shape("tiny")
+    circ = circuits.Circuit(shape, O.OracleBackend, seed=1)
+    S, n = len(shape.perm_columns), shape.n
+    mc = np.zeros(S * n, dtype=np.uint32); mr = np.zeros(S * n, dtype=np.uint32)
+    assert hl.hl_perm_mapping(circ.blob, C.c_size_t(len(circ.blob)), mc.ctypes.data_as(C.c_void_p), mr.ctypes.data_as(C.c_void_p)) == 0
+    nxt = mc.astype(np.int64) * n + mr
+    assert sorted(nxt.tolist()) == list(range(S * n))                 # sigma is a permutation of the cells
+    # every copy constraint joins its two cells into one cycle
+    cyc = -np.ones(S * n, dtype=np.int64)
+    for start in range(S * n):
+        if cyc[start] >= 0:
+            continue
+        i = start
+        while cyc[i] < 0:
+            cyc[i] = start
+            i = nxt[i]
+    for lc, lr, rc, rr in circ.copies:
+        assert cyc[lc * n + lr] == cyc[rc * n + rr]
+    # cells without copy constraints map to themselves
+    touched = set()
+    for lc, lr, rc, rr in circ.copies:
+        touched.add(lc * n + lr); touched.add(rc * n + rr)
+    free = np.array([i for i in range(S * n) if i not in touched])
+    assert np.array_equal(nxt[free], free)

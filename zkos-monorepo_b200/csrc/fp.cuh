@@ -121,6 +121,7 @@ __device__ __forceinline__ Fe<Tag> fe_load(const Fe<Tag>* p) {
     r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
     return r;
 }
+#ifdef __CUDACC__
 template <class Tag>
 __device__ __forceinline__ Fe<Tag> fe_ldg(const Fe<Tag>* p) {  // read-only path
     const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -130,6 +131,7 @@ __device__ __forceinline__ Fe<Tag> fe_ldg(const Fe<Tag>* p) {  // read-only path
     r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
     return r;
 }
+#endif
 template <class Tag>
 __device__ __forceinline__ void fe_store(Fe<Tag>* p, const Fe<Tag>& v) {
     uint4* q = reinterpret_cast<uint4*>(p);
