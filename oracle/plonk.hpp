@@ -46,7 +46,9 @@ struct ConstraintSystem {
     std::vector<Expr> gates;
     std::vector<Fr> constants;
     std::vector<ColumnRef> perm_columns;
-    uint32_t num_lookups = 0;
+    struct Lookup { std::vector<Expr> inputs, tables; };
+    std::vector<Lookup> lookups;
+    size_t num_lookups() const { return lookups.size(); }
 
     size_t n() const { return (size_t)1 << k; }
     static unsigned expr_degree(const Expr& e) {
@@ -61,8 +63,15 @@ struct ConstraintSystem {
         return st.empty() ? 0 : st.back();
     }
     // ConstraintSystem::degree(): permutation needs 3, gates their own degree
+    // ConstraintSystem::degree(): permutation needs 3, a lookup max(4, 2 + input_degree + table_degree), gates their own
     unsigned degree() const {
         unsigned d = perm_columns.empty() ? 1 : 3;
+        for (auto& l : lookups) {
+            unsigned di = 1, dt = 1;
+            for (auto& e : l.inputs) di = std::max(di, expr_degree(e));
+            for (auto& e : l.tables) dt = std::max(dt, expr_degree(e));
+            d = std::max(d, std::max(4u, 2 + di + dt));
+        }
         for (auto& g : gates) d = std::max(d, expr_degree(g));
         return d;
     }
@@ -80,10 +89,11 @@ struct ConstraintSystem {
     int rotation_last() const { return -(int)(blinding_factors() + 1); }
     size_t usable_rows() const { return n() - (blinding_factors() + 1); }
     size_t num_evals() const {
-        return advice_queries.size() + fixed_queries.size() + 1 + perm_columns.size() + (num_perm_sets() ? 3 * num_perm_sets() - 1 : 0);
+        return advice_queries.size() + fixed_queries.size() + 1 + perm_columns.size() + (num_perm_sets() ? 3 * num_perm_sets() - 1 : 0) + 5 * num_lookups();
     }
+    // crates/halo2-verifier/src/lib/codegen/util.rs:175-186
     size_t proof_len() const {
-        return 64 * (num_advice + num_perm_sets() + 1 + num_quotients()) + 32 * num_evals() + 128;
+        return 64 * (num_advice + 3 * num_lookups() + num_perm_sets() + 1 + num_quotients()) + 32 * num_evals() + 128;
     }
 };
 
@@ -111,8 +121,13 @@ static inline Circuit parse_circuit(const uint8_t* data, size_t len) {
     uint32_t ng = r.u32(); cs.gates.resize(ng);
     for (auto& g : cs.gates) { uint32_t m = r.u32(); g.resize(m); for (auto& i : g) { i.op = r.u32(); i.arg = r.u32(); } }
     uint32_t np = r.u32(); cs.perm_columns.resize(np); for (auto& pc : cs.perm_columns) { pc.type = r.u32(); pc.index = r.u32(); }
-    cs.num_lookups = r.u32();
-    if (cs.num_lookups) throw std::runtime_error("lookups are not supported yet");
+    auto rexpr = [&](Expr& g) { uint32_t m = r.u32(); g.resize(m); for (auto& i : g) { i.op = r.u32(); i.arg = r.u32(); } };
+    cs.lookups.resize(r.u32());
+    for (auto& l : cs.lookups) {
+        l.inputs.resize(r.u32()); for (auto& e : l.inputs) rexpr(e);
+        l.tables.resize(r.u32()); for (auto& e : l.tables) rexpr(e);
+        if (l.inputs.empty() || l.inputs.size() != l.tables.size()) throw std::runtime_error("lookup: input/table expression counts differ");
+    }
     if (cs.num_instance != 1) throw std::runtime_error("exactly one instance column is supported (as Shielder's circuits)");
     size_t n = cs.n();
     c.fixed.assign(cs.num_fixed, std::vector<Fr>(n, Fr::zero()));
@@ -305,6 +320,26 @@ static inline std::string check_witness(const Circuit& c, const std::vector<std:
     };
     for (auto& cp : c.copies)
         if (cell(cp.lcol, cp.lrow) != cell(cp.rcol, cp.rrow)) return "copy constraint violated";
+    // lookups: every input tuple of a usable row appears among the table tuples of the usable rows
+    for (size_t l = 0; l < cs.lookups.size(); ++l) {
+        auto tuple_at = [&](const std::vector<Expr>& exprs, size_t row) {
+            std::vector<U256> t;
+            for (auto& e : exprs)
+                t.push_back(eval_expr(e, cs.constants,
+                    [&](uint32_t q) { return c.fixed[cs.fixed_queries[q].column][rot(row, cs.fixed_queries[q].rotation)]; },
+                    [&](uint32_t q) { return advice[cs.advice_queries[q].column][rot(row, cs.advice_queries[q].rotation)]; },
+                    [&](uint32_t q) { return inst[rot(row, cs.instance_queries[q].rotation)]; }).to_u256());
+            return t;
+        };
+        auto less = [](const std::vector<U256>& a, const std::vector<U256>& b) {
+            for (size_t i = 0; i < a.size(); ++i) { int c_ = u256_cmp(a[i], b[i]); if (c_) return c_ < 0; }
+            return false;
+        };
+        std::set<std::vector<U256>, decltype(less)> table(less);
+        for (size_t row = 0; row < usable; ++row) table.insert(tuple_at(cs.lookups[l].tables, row));
+        for (size_t row = 0; row < usable; ++row)
+            if (!table.count(tuple_at(cs.lookups[l].inputs, row))) return "lookup " + std::to_string(l) + " not satisfied at row " + std::to_string(row);
+    }
     return "";
 }
 
@@ -315,21 +350,32 @@ static inline std::string check_witness(const Circuit& c, const std::vector<std:
 struct OpenQuery { int comm; int rot; int eval; };  // comm: commitment id; eval: index into the eval list
 struct RotationSet { std::vector<int> rots, diffs; std::vector<int> comms; std::vector<std::vector<int>> evals; };
 
-// commitment ids: [0,A) advice, then perm z sets, then fixed, then sigma, then H, then RANDOM
+// commitment ids: [0,A) advice | P permutation z | L lookup z | L permuted inputs | L permuted tables | F fixed | S sigma | H | RANDOM
 struct QueryPlan {
     std::vector<OpenQuery> queries;
     std::vector<int> superset;  // sorted rotations
     std::vector<RotationSet> sets;
-    int id_perm_z0, id_fixed0, id_sigma0, id_h, id_random, num_comms;
+    int id_perm_z0, id_lk_z0, id_lk_a0, id_lk_s0, id_fixed0, id_sigma0, id_h, id_random, num_comms;
+    int e_lookup0;
     // eval indices (positions in the proof's evaluation list); h eval is "computed": index = num_evals
     explicit QueryPlan(const ConstraintSystem& cs) {
-        int A = cs.num_advice, P = cs.num_perm_sets(), F = cs.num_fixed, S = (int)cs.perm_columns.size();
-        id_perm_z0 = A; id_fixed0 = A + P; id_sigma0 = A + P + F; id_h = A + P + F + S; id_random = id_h + 1; num_comms = id_random + 1;
+        int A = cs.num_advice, P = cs.num_perm_sets(), F = cs.num_fixed, S = (int)cs.perm_columns.size(), L = (int)cs.num_lookups();
+        id_perm_z0 = A; id_lk_z0 = A + P; id_lk_a0 = id_lk_z0 + L; id_lk_s0 = id_lk_a0 + L; id_fixed0 = id_lk_s0 + L; id_sigma0 = id_fixed0 + F;
+        id_h = id_sigma0 + S; id_random = id_h + 1; num_comms = id_random + 1;
         int e_adv = 0, e_fix = (int)cs.advice_queries.size(), e_rand = e_fix + (int)cs.fixed_queries.size(), e_sigma = e_rand + 1, e_z = e_sigma + S;
+        e_lookup0 = e_z + (P ? 3 * P - 1 : 0);
         int e_h = (int)cs.num_evals();
         for (size_t i = 0; i < cs.advice_queries.size(); ++i) queries.push_back({(int)cs.advice_queries[i].column, cs.advice_queries[i].rotation, e_adv + (int)i});
         for (int s = 0; s < P; ++s) { queries.push_back({id_perm_z0 + s, 0, e_z + 3 * s}); queries.push_back({id_perm_z0 + s, 1, e_z + 3 * s + 1}); }
         for (int s = P - 2; s >= 0; --s) queries.push_back({id_perm_z0 + s, cs.rotation_last(), e_z + 3 * s + 2});
+        for (int l = 0; l < L; ++l) {  // codegen/pcs.rs:80-92
+            int e = e_lookup0 + 5 * l;
+            queries.push_back({id_lk_z0 + l, 0, e});
+            queries.push_back({id_lk_a0 + l, 0, e + 2});
+            queries.push_back({id_lk_s0 + l, 0, e + 4});
+            queries.push_back({id_lk_a0 + l, -1, e + 3});
+            queries.push_back({id_lk_z0 + l, 1, e + 1});
+        }
         for (size_t i = 0; i < cs.fixed_queries.size(); ++i) queries.push_back({id_fixed0 + (int)cs.fixed_queries[i].column, cs.fixed_queries[i].rotation, e_fix + (int)i});
         for (int s = 0; s < S; ++s) queries.push_back({id_sigma0 + s, 0, e_sigma + s});
         queries.push_back({id_h, 0, e_h});
@@ -416,7 +462,61 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
     trace2("advice_blinded", advice);
     for (auto& col : advice) { tr.write_point(params.commit_lagrange(col)); st.msms++; }
 
-    Fr theta = tr.squeeze_challenge(); (void)theta;
+    Fr theta = tr.squeeze_challenge();
+
+    // lookup arguments, part 1 (halo2 lookup/prover.rs commit_permuted): compress the input / table expressions with
+    // theta over the Lagrange rows, permute the pair, blind, commit
+    const size_t L = cs.num_lookups();
+    std::vector<std::vector<Fr>> lk_in(L), lk_tab(L), lk_a(L), lk_s(L);  // compressed input/table, permuted input/table (values)
+    {
+        auto rotl = [&](size_t row, int r) { return (size_t)(((long)row + r) % (long)n + (long)n) % n; };
+        auto compress = [&](const std::vector<Expr>& exprs) {
+            std::vector<Fr> out(n, Fr::zero());
+            for (auto& e : exprs)
+                for (size_t row = 0; row < n; ++row) {
+                    Fr v = eval_expr(e, cs.constants,
+                        [&](uint32_t q) { return pk.fixed_values[cs.fixed_queries[q].column][rotl(row, cs.fixed_queries[q].rotation)]; },
+                        [&](uint32_t q) { return advice[cs.advice_queries[q].column][rotl(row, cs.advice_queries[q].rotation)]; },
+                        [&](uint32_t q) { return instance_values[rotl(row, cs.instance_queries[q].rotation)]; });
+                    out[row] = out[row] * theta + v;
+                }
+            return out;
+        };
+        for (size_t l = 0; l < L; ++l) {
+            lk_in[l] = compress(cs.lookups[l].inputs);
+            lk_tab[l] = compress(cs.lookups[l].tables);
+            // permute_expression_pair
+            std::vector<Fr> a(lk_in[l].begin(), lk_in[l].begin() + unusable_start);
+            // `Fr: Ord` compares canonical representations (halo2curves derive/field.rs)
+            std::sort(a.begin(), a.end(), [](const Fr& x, const Fr& y) { return u256_cmp(x.to_u256(), y.to_u256()) < 0; });
+            struct U256Less { bool operator()(const U256& x, const U256& y) const { return u256_cmp(x, y) < 0; } };
+            std::map<U256, uint32_t, U256Less> leftover;  // BTreeMap<Fr, u32>: iteration in ascending canonical order
+            for (size_t i = 0; i < unusable_start; ++i) leftover[lk_tab[l][i].to_u256()]++;
+            std::vector<Fr> pt(unusable_start, Fr::zero());
+            std::vector<size_t> repeated;
+            for (size_t row = 0; row < unusable_start; ++row) {
+                if (row == 0 || a[row] != a[row - 1]) {
+                    pt[row] = a[row];
+                    auto it = leftover.find(a[row].to_u256());
+                    if (it == leftover.end() || it->second == 0) throw std::runtime_error("create_proof: lookup input not in table (ConstraintSystemFailure)");
+                    it->second--;
+                } else repeated.push_back(row);
+            }
+            for (auto& kv : leftover)
+                for (uint32_t c = 0; c < kv.second; ++c) { pt[repeated.back()] = Fr::from_u256(kv.first); repeated.pop_back(); }
+            if (!repeated.empty()) throw std::runtime_error("create_proof: lookup permutation mismatch");
+            for (size_t i = unusable_start; i < n; ++i) a.push_back(random_field<Fr>(rng));
+            for (size_t i = unusable_start; i < n; ++i) pt.push_back(random_field<Fr>(rng));
+            (void)random_field<Fr>(rng);  // Blind of the permuted input commitment
+            (void)random_field<Fr>(rng);  // Blind of the permuted table commitment
+            tr.write_point(params.commit_lagrange(a)); st.msms++;
+            tr.write_point(params.commit_lagrange(pt)); st.msms++;
+            lk_a[l] = std::move(a); lk_s[l] = std::move(pt);
+        }
+        trace2("lookup_permuted_input", lk_a);
+        trace2("lookup_permuted_table", lk_s);
+    }
+
     Fr beta = tr.squeeze_challenge(), gamma = tr.squeeze_challenge();
 
     // permutation grand products
@@ -453,6 +553,28 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
             z_cosets.push_back(d.coeff_to_extended(zc)); st.ext_ntts++;
             z_polys.push_back(std::move(zc));
         }
+    }
+
+    // lookup arguments, part 2 (commit_product): z[0] = 1, z[i+1] = z[i] (A_i + beta)(S_i + gamma) / ((A'_i + beta)(S'_i + gamma))
+    std::vector<std::vector<Fr>> lk_z_polys(L), lk_a_polys(L), lk_s_polys(L), lk_z_cosets(L), lk_a_cosets(L), lk_s_cosets(L);
+    for (size_t l = 0; l < L; ++l) {
+        std::vector<Fr> den(n);
+        for (size_t i = 0; i < n; ++i) den[i] = (beta + lk_a[l][i]) * (gamma + lk_s[l][i]);
+        batch_invert(den.data(), n);
+        for (size_t i = 0; i < n; ++i) den[i] = den[i] * (lk_in[l][i] + beta) * (lk_tab[l][i] + gamma);
+        std::vector<Fr> z(n);
+        z[0] = Fr::one();
+        for (size_t row = 1; row < n - bf; ++row) z[row] = z[row - 1] * den[row - 1];
+        for (size_t i = n - bf; i < n; ++i) z[i] = random_field<Fr>(rng);
+        (void)random_field<Fr>(rng);  // Blind
+        trace("lookup_z", z);
+        tr.write_point(params.commit_lagrange(z)); st.msms++;
+        lk_z_polys[l] = d.lagrange_to_coeff(z); st.ntts++;
+        lk_a_polys[l] = d.lagrange_to_coeff(lk_a[l]); st.ntts++;
+        lk_s_polys[l] = d.lagrange_to_coeff(lk_s[l]); st.ntts++;
+        lk_z_cosets[l] = d.coeff_to_extended(lk_z_polys[l]); st.ext_ntts++;
+        lk_a_cosets[l] = d.coeff_to_extended(lk_a_polys[l]); st.ext_ntts++;
+        lk_s_cosets[l] = d.coeff_to_extended(lk_s_polys[l]); st.ext_ntts++;
     }
 
     // vanishing argument: random polynomial (single-thread ChaCha20 stream)
@@ -519,6 +641,25 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
                         v = v * y + (left - right) * pk.l_active_row[i];
                     }
                 }
+                for (size_t l = 0; l < L; ++l) {
+                    size_t r_next = ridx(i, 1), r_prev = ridx(i, -1);
+                    auto compress = [&](const std::vector<Expr>& exprs) {
+                        Fr acc = Fr::zero();
+                        for (auto& e : exprs)
+                            acc = acc * theta + eval_expr(e, cs.constants,
+                                [&](uint32_t q) { return pk.fixed_cosets[cs.fixed_queries[q].column][ridx(i, cs.fixed_queries[q].rotation)]; },
+                                [&](uint32_t q) { return advice_cosets[cs.advice_queries[q].column][ridx(i, cs.advice_queries[q].rotation)]; },
+                                [&](uint32_t q) { return instance_cosets[0][ridx(i, cs.instance_queries[q].rotation)]; });
+                        return acc;
+                    };
+                    const Fr& z = lk_z_cosets[l][i]; const Fr& a = lk_a_cosets[l][i]; const Fr& sp = lk_s_cosets[l][i];
+                    Fr a_minus_s = a - sp;
+                    v = v * y + (one - z) * pk.l0[i];
+                    v = v * y + (z.square() - z) * pk.l_last[i];
+                    v = v * y + (lk_z_cosets[l][r_next] * (a + beta) * (sp + gamma) - z * (compress(cs.lookups[l].inputs) + beta) * (compress(cs.lookups[l].tables) + gamma)) * pk.l_active_row[i];
+                    v = v * y + a_minus_s * pk.l0[i];
+                    v = v * y + a_minus_s * (a - lk_a_cosets[l][r_prev]) * pk.l_active_row[i];
+                }
                 h[i] = v;
             }
         });
@@ -551,6 +692,13 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
         evals.push_back(eval_polynomial(z_polys[s].data(), n, d.rotate_omega(x, 1)));
         if (s + 1 < z_polys.size()) evals.push_back(eval_polynomial(z_polys[s].data(), n, d.rotate_omega(x, cs.rotation_last())));
     }
+    for (size_t l = 0; l < L; ++l) {
+        evals.push_back(eval_polynomial(lk_z_polys[l].data(), n, x));
+        evals.push_back(eval_polynomial(lk_z_polys[l].data(), n, d.rotate_omega(x, 1)));
+        evals.push_back(eval_polynomial(lk_a_polys[l].data(), n, x));
+        evals.push_back(eval_polynomial(lk_a_polys[l].data(), n, d.rotate_omega(x, -1)));
+        evals.push_back(eval_polynomial(lk_s_polys[l].data(), n, x));
+    }
     trace("evals", evals);
     trace("h_poly", h_poly);
     for (auto& e : evals) tr.write_scalar(e);
@@ -560,7 +708,10 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
     QueryPlan plan(cs);
     auto poly_of = [&](int id) -> const std::vector<Fr>& {
         if (id < plan.id_perm_z0) return advice_polys[id];
-        if (id < plan.id_fixed0) return z_polys[id - plan.id_perm_z0];
+        if (id < plan.id_lk_z0) return z_polys[id - plan.id_perm_z0];
+        if (id < plan.id_lk_a0) return lk_z_polys[id - plan.id_lk_z0];
+        if (id < plan.id_lk_s0) return lk_a_polys[id - plan.id_lk_a0];
+        if (id < plan.id_fixed0) return lk_s_polys[id - plan.id_lk_s0];
         if (id < plan.id_sigma0) return pk.fixed_polys[id - plan.id_fixed0];
         if (id < plan.id_h) return pk.perm_polys[id - plan.id_sigma0];
         return id == plan.id_h ? h_poly : random_poly;
@@ -640,11 +791,14 @@ static inline bool verify_proof_to_pairing(const ParamsKZG& params, const Verify
     for (auto& v : instance) tr.common_scalar(v);
     bool ok = true;
     const unsigned A = cs.num_advice, P = cs.num_perm_sets(), Q = cs.num_quotients();
-    std::vector<G1Affine> advice_c(A), z_c(P), h_c(Q); G1Affine random_c, W, Wp;
+    const size_t L = cs.num_lookups();
+    std::vector<G1Affine> advice_c(A), z_c(P), h_c(Q), lk_a_c(L), lk_s_c(L), lk_z_c(L); G1Affine random_c, W, Wp;
     for (auto& p : advice_c) ok &= tr.read_point(p);
-    Fr theta = tr.squeeze_challenge(); (void)theta;
+    Fr theta = tr.squeeze_challenge();
+    for (size_t l = 0; l < L; ++l) { ok &= tr.read_point(lk_a_c[l]); ok &= tr.read_point(lk_s_c[l]); }
     Fr beta = tr.squeeze_challenge(), gamma = tr.squeeze_challenge();
     for (auto& p : z_c) ok &= tr.read_point(p);
+    for (auto& p : lk_z_c) ok &= tr.read_point(p);
     ok &= tr.read_point(random_c);
     Fr y = tr.squeeze_challenge();
     for (auto& p : h_c) ok &= tr.read_point(p);
@@ -712,6 +866,29 @@ static inline bool verify_proof_to_pairing(const ParamsKZG& params, const Verify
             numer = numer * y + (lsr - lsr * (l_last + l_blind));
         }
     }
+    // lookup terms (codegen/evaluator.rs:126-223)
+    {
+        const size_t e_lk = e_z + (P ? 3 * P - 1 : 0);
+        Fr l_active = Fr::one() - (l_blind + l_last);
+        auto compress = [&](const std::vector<Expr>& exprs) {
+            Fr acc = Fr::zero();
+            for (auto& e : exprs)
+                acc = acc * theta + eval_expr(e, cs.constants, [&](uint32_t q) { return evals[e_fix + q]; }, [&](uint32_t q) { return evals[q]; },
+                                              [&](uint32_t) { return instance_eval; });
+            return acc;
+        };
+        for (size_t l = 0; l < L; ++l) {
+            const Fr &z = evals[e_lk + 5 * l], &z_next = evals[e_lk + 5 * l + 1], &p_in = evals[e_lk + 5 * l + 2], &p_in_prev = evals[e_lk + 5 * l + 3],
+                     &p_tab = evals[e_lk + 5 * l + 4];
+            numer = numer * y + (l_0 - l_0 * z);
+            numer = numer * y + l_last * (z * z - z);
+            Fr lhs = z_next * ((p_in + beta) * (p_tab + gamma));
+            Fr rhs = z * ((compress(cs.lookups[l].inputs) + beta) * (compress(cs.lookups[l].tables) + gamma));
+            numer = numer * y + l_active * (lhs - rhs);
+            numer = numer * y + l_0 * (p_in - p_tab);
+            numer = numer * y + l_active * ((p_in - p_tab) * (p_in - p_in_prev));
+        }
+    }
     Fr quotient_eval = numer * xn_m1_inv;
 
     // quotient commitment (Halo2Verifier.sol:494-512)
@@ -724,7 +901,10 @@ static inline bool verify_proof_to_pairing(const ParamsKZG& params, const Verify
     std::vector<Fr> all_evals = evals; all_evals.push_back(quotient_eval);
     auto comm_of = [&](int id) -> G1Affine {
         if (id < plan.id_perm_z0) return advice_c[id];
-        if (id < plan.id_fixed0) return z_c[id - plan.id_perm_z0];
+        if (id < plan.id_lk_z0) return z_c[id - plan.id_perm_z0];
+        if (id < plan.id_lk_a0) return lk_z_c[id - plan.id_lk_z0];
+        if (id < plan.id_lk_s0) return lk_a_c[id - plan.id_lk_a0];
+        if (id < plan.id_fixed0) return lk_s_c[id - plan.id_lk_s0];
         if (id < plan.id_sigma0) return vk.fixed_commitments[id - plan.id_fixed0];
         if (id < plan.id_h) return vk.perm_commitments[id - plan.id_sigma0];
         return id == plan.id_h ? quotient_c : random_c;

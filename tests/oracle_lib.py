@@ -212,6 +212,10 @@ class OracleBackend:
         return to_mont(0, pyref.int_to_limbs([v % pyref.R_MOD]))[0]
 
     @staticmethod
+    def to_mont(canon):
+        return to_mont(0, canon).reshape(-1, 4)
+
+    @staticmethod
     def mul(a, b):
         return field_op(0, 0, a, b).reshape(-1, 4)
 

@@ -81,3 +81,32 @@ def test_prove_verify_bigger_shape(name):
     assert ok, msg
     proof = po.prove(adv, pi, seed=42)
     assert po.verify(proof, pi)
+
+
+@pytest.mark.parametrize("name", ["tiny_lookup", "small_lookup"])
+def test_lookup_circuits_prove_verify(name):
+    """Lookup arguments (verifier terms codegen/evaluator.rs:126-223): one- and
+    two-expression lookups, prove -> verify, metadata, negative cases."""
+    shape = circuits.Shape(name)
+    circ = circuits.Circuit(shape, O.OracleBackend, seed=2)
+    po = O.PlonkOracle(circ.blob, O.downsized_srs(shape.k), threads=4)
+    assert po.degree == shape.degree and po.blinding_factors == shape.blinding_factors
+    assert po.num_evals == shape.num_evals and po.proof_len == shape.proof_len and po.extended_k == shape.extended_k
+    adv, pi = circ.witness(7)
+    ok, msg = po.check_witness(adv, pi)
+    assert ok, msg
+    proof = po.prove(adv, pi, seed=42)
+    assert len(proof) == shape.proof_len
+    assert po.last_stats == dict(msm=shape.num_msm, ntt=shape.num_ntt, ext_ntt=shape.num_ext_ntt)
+    assert po.verify(proof, pi)
+    assert po.prove(adv, pi, seed=42) == proof
+    for pos in (5, 64 * shape.num_advice + 7, 64 * (shape.num_advice + 2 * shape.n_lookup) + 9, len(proof) - 300, len(proof) - 1):
+        b = bytearray(proof); b[pos] ^= 0x01
+        assert not po.verify(bytes(b), pi), pos
+    # a value outside the table: MockProver-style check fails and create_proof reports ConstraintSystemFailure
+    bad = adv.copy()
+    bad[shape.lv[0], 3] = O.OracleBackend.const(shape.table_size + 5)
+    ok, msg = po.check_witness(bad, pi)
+    assert not ok and "lookup" in msg
+    with pytest.raises(RuntimeError):
+        po.prove(bad, pi, seed=1)

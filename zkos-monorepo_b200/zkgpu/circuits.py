@@ -5,7 +5,8 @@ and cannot be reproduced here, so configs 1/4/5 run on shape-equivalent syntheti
 of arithmetic units (q_m*a*b + q_l*a + q_r*b + q_o*c + q_c + q_pi*PI = 0) chained by copy constraints
 and Poseidon-style power-5 units (q_pow * ((x + rc)^5 + y - x_next) = 0, degree 6 => 5 quotient
 pieces, extended domain 2^(k+3)), one instance column that takes part in the permutation argument,
-no lookups.  This module builds the constraint-system blob both libzkgpu and the CPU oracle parse,
+and optionally range-check style lookup arguments (`n_lookup`: lookup 0 is q_lk*v in {0..T-1}; lookup 1 compresses two
+expressions, (q_lk*v, q_lk*w) in {(i, 3i+1)} u {(0,0)}, so theta is exercised).  This module builds the constraint-system blob both libzkgpu and the CPU oracle parse,
 and satisfying witnesses.  Field arithmetic is delegated to an injected backend (vectorised
 mul/add/sub over (n,4) uint64 Montgomery arrays): the tests inject the CPU oracle, bench.py injects
 the GPU library, so this file never touches the oracle itself.
@@ -27,6 +28,10 @@ SHAPES = {
     # small shapes for fast CPU tests
     "tiny": dict(k=6, n_arith=2, n_pow=1, num_pi=3),
     "small": dict(k=9, n_arith=3, n_pow=2, num_pi=8),
+    # the same families with lookup arguments
+    "tiny_lookup": dict(k=6, n_arith=2, n_pow=1, num_pi=3, n_lookup=2, table_size=16),
+    "small_lookup": dict(k=9, n_arith=3, n_pow=0, num_pi=8, n_lookup=1, table_size=64),
+    "withdraw_lookup": dict(k=13, n_arith=6, n_pow=3, num_pi=8, n_lookup=2, table_size=256),
 }
 
 FIXED_NAMES = ["q_m", "q_l", "q_r", "q_o", "q_c", "q_pi", "q_pow", "rc"]
@@ -38,9 +43,15 @@ class Shape:
         p.update(kw)
         self.name = name or "custom"
         self.k, self.n_arith, self.n_pow, self.num_pi = p["k"], p["n_arith"], p["n_pow"], p["num_pi"]
+        self.n_lookup, self.table_size = p.get("n_lookup", 0), p.get("table_size", 0)
+        assert self.n_lookup in (0, 1, 2)
         self.n = 1 << self.k
-        self.num_advice = 3 * self.n_arith + 2 * self.n_pow
-        self.num_fixed = len(FIXED_NAMES)
+        self.num_advice = 3 * self.n_arith + 2 * self.n_pow + (0, 1, 3)[self.n_lookup]
+        self.fixed_names = FIXED_NAMES + (["q_lk", "t_a", "t_b"] if self.n_lookup else [])
+        self.num_fixed = len(self.fixed_names)
+        base = 3 * self.n_arith + 2 * self.n_pow
+        self.lv = [base, base + 1][: self.n_lookup]      # looked-up value columns
+        self.lw = base + 2 if self.n_lookup == 2 else None
         # advice column indices
         self.a = [3 * u for u in range(self.n_arith)]
         self.b = [3 * u + 1 for u in range(self.n_arith)]
@@ -51,7 +62,7 @@ class Shape:
         self.advice_queries = [(c, 0) for c in range(self.num_advice)] + [(c, 1) for c in self.x]
         self.fixed_queries = [(c, 0) for c in range(self.num_fixed)]
         self.instance_queries = [(0, 0)]
-        self.degree = 6 if self.n_pow else 3
+        self.degree = max(6 if self.n_pow else 3, 5 if self.n_lookup else 0)   # lookup: max(4, 2 + deg(q_lk*v) + deg(t))
         max_q = 2 if self.n_pow else 1
         self.blinding_factors = max(3, max_q) + 2
         self.usable = self.n - (self.blinding_factors + 1)
@@ -63,16 +74,29 @@ class Shape:
         self.extended_k = self.k
         while (1 << self.extended_k) < self.n * (self.degree - 1):
             self.extended_k += 1
+        L = self.n_lookup
         self.num_evals = (len(self.advice_queries) + len(self.fixed_queries) + 1 + len(self.perm_columns)
-                          + 3 * self.num_perm_sets - 1)
-        self.proof_len = 64 * (self.num_advice + self.num_perm_sets + 1 + self.num_quotients) + 32 * self.num_evals + 128
-        self.num_msm = self.num_advice + self.num_perm_sets + self.num_quotients + 3
-        self.num_ntt = 1 + self.num_advice + self.num_perm_sets
-        self.num_ext_ntt = self.num_advice + 1 + self.num_perm_sets + 1
+                          + 3 * self.num_perm_sets - 1 + 5 * L)
+        self.proof_len = 64 * (self.num_advice + 3 * L + self.num_perm_sets + 1 + self.num_quotients) + 32 * self.num_evals + 128
+        self.num_msm = self.num_advice + 3 * L + self.num_perm_sets + self.num_quotients + 3
+        self.num_ntt = 1 + self.num_advice + 3 * L + self.num_perm_sets
+        self.num_ext_ntt = self.num_advice + 1 + 3 * L + self.num_perm_sets + 1
 
     # ---- expressions (postfix) -------------------------------------------------------------
+    def lookups(self):
+        """[(input expressions, table expressions)] in postfix form"""
+        F = {n: i for i, n in enumerate(self.fixed_names)}
+        aq = {q: i for i, q in enumerate(self.advice_queries)}
+        sel = lambda col: [(OP_FIXED, F["q_lk"]), (OP_ADVICE, aq[(col, 0)]), (OP_MUL, 0)]
+        out = []
+        if self.n_lookup >= 1:
+            out.append(([sel(self.lv[0])], [[(OP_FIXED, F["t_a"])]]))
+        if self.n_lookup == 2:
+            out.append(([sel(self.lv[1]), sel(self.lw)], [[(OP_FIXED, F["t_a"])], [(OP_FIXED, F["t_b"])]]))
+        return out
+
     def gates(self):
-        F = {n: i for i, n in enumerate(FIXED_NAMES)}
+        F = {n: i for i, n in enumerate(self.fixed_names)}
         aq = {q: i for i, q in enumerate(self.advice_queries)}
         gates = []
         for u in range(self.n_arith):
@@ -122,7 +146,16 @@ class Circuit:
         even = np.arange(n) % 2 == 0
         q_pow[even & (np.arange(n) + 1 < usable)] = one
         fx["q_pow"] = q_pow
-        self.fixed = np.stack([fx[nm] for nm in FIXED_NAMES])  # (F, n, 4)
+        if s.n_lookup:
+            T = s.table_size
+            assert T < usable
+            fx["q_lk"] = np.where(active[:, None], one[None, :], zero)
+            idx = np.zeros((n, 4), dtype=np.uint64)
+            idx[:T, 0] = np.arange(T, dtype=np.uint64)
+            tb = np.zeros((n, 4), dtype=np.uint64)
+            tb[:T, 0] = 3 * np.arange(T, dtype=np.uint64) + 1
+            fx["t_a"], fx["t_b"] = F.to_mont(idx), F.to_mont(tb)
+        self.fixed = np.stack([fx[nm] for nm in s.fixed_names])  # (F, n, 4)
         # copy constraints (indices into perm_columns: advice column c -> c, instance -> num_advice)
         copies = []
         for u in range(1, s.n_arith):
@@ -151,7 +184,14 @@ class Circuit:
         out.append(struct.pack("<I", len(s.perm_columns)))
         for t, i in s.perm_columns:
             out.append(struct.pack("<II", t, i))
-        out.append(struct.pack("<I", 0))  # lookups
+        lks = s.lookups()
+        out.append(struct.pack("<I", len(lks)))
+        for inputs, tables in lks:
+            for exprs in (inputs, tables):
+                out.append(struct.pack("<I", len(exprs)))
+                for e in exprs:
+                    out.append(struct.pack("<I", len(e)))
+                    out.append(np.array(e, dtype=np.uint32).tobytes())
         out.append(np.ascontiguousarray(self.fixed).tobytes())
         out.append(struct.pack("<I", len(self.copies)))
         out.append(np.array(self.copies, dtype=np.uint32).tobytes())
@@ -162,7 +202,7 @@ class Circuit:
         """Returns (advice (A, n, 4) uint64 Montgomery, instance (num_pi, 4)) satisfying the circuit."""
         s, F = self.shape, self.F
         n, usable = s.n, s.usable
-        fx = {nm: self.fixed[i] for i, nm in enumerate(FIXED_NAMES)}
+        fx = {nm: self.fixed[i] for i, nm in enumerate(s.fixed_names)}
         need = s.n_arith + 1 + 2 * s.n_pow
         rnd = F.random(0x9E3779B9 * (seed + 1) & 0xFFFFFFFFFFFF, need * n + s.num_pi)
         take = iter(range(need))
@@ -194,5 +234,15 @@ class Circuit:
             nxt = F.add(F.mul(F.mul(t2, t2), t), y)  # value required at row+1 wherever q_pow = 1
             x[1:][even[:-1]] = nxt[:-1][even[:-1]]
             adv[s.x[v]], adv[s.y[v]] = x, y
+        if s.n_lookup:
+            lrng = np.random.default_rng(seed * 7919 + 13)
+            for l, col in enumerate(s.lv):
+                v = np.zeros((n, 4), dtype=np.uint64)
+                v[:usable, 0] = lrng.integers(0, s.table_size, usable, dtype=np.uint64)
+                adv[col] = F.to_mont(v)
+                if l == 1:
+                    w = np.zeros((n, 4), dtype=np.uint64)
+                    w[:usable, 0] = 3 * v[:usable, 0] + 1
+                    adv[s.lw] = F.to_mont(w)
         adv[:, usable:] = 0  # unusable rows are overwritten with blinding by the prover
         return adv, pi

@@ -36,6 +36,13 @@ class GpuBackend:
         return out[0]
 
     @staticmethod
+    def to_mont(canon):
+        canon = _u64(canon).reshape(-1, 4)
+        out = np.empty_like(canon)
+        _chk(lib().zkgpu_fr_to_mont(_p(canon), _p(out), C.c_size_t(canon.shape[0])))
+        return out
+
+    @staticmethod
     def mul(a, b):
         return _vec_op(0, a, b)
 
