@@ -205,3 +205,29 @@ def test_gpu_field_backend_builds_identical_circuits():
     assert a.blob == b.blob
     wa, wb = a.witness(9), b.witness(9)
     assert np.array_equal(wa[0], wb[0]) and np.array_equal(wa[1], wb[1])
+
+
+@pytest.mark.parametrize("name,k,count", [("tiny_lookup", None, 3), ("small_lookup", None, 2), ("withdraw_lookup", 11, 2)])
+def test_lookup_circuits_match_oracle(name, k, count):
+    """Lookup arguments on the GPU (theta compression, bitonic sort + permute_expression_pair, lookup grand
+    product, quotient terms, SHPLONK queries): byte-identical to the oracle, accepted by the verifier."""
+    zkgpu.init(0)
+    shape = circuits.Shape(name, k=k) if k else circuits.Shape(name)
+    circ = circuits.Circuit(shape, O.OracleBackend, seed=4)
+    srs = O.downsized_srs(shape.k)
+    po = O.PlonkOracle(circ.blob, srs, threads=8)
+    params = zkgpu.ParamsKZG(shape.k, srs["g"], srs["g_lagrange"])
+    pk = zkgpu.ProvingKey(params, circ.blob)
+    try:
+        assert (pk.degree, pk.num_evals, pk.proof_len) == (shape.degree, shape.num_evals, shape.proof_len)
+        _check_batch(shape, circ, po, pk, seeds=list(range(7, 7 + count)), witness_seeds=list(range(20, 20 + count)), traced=True)
+        # an input outside the table: upstream returns Error::ConstraintSystemFailure
+        adv, pi = circ.witness(1)
+        adv[shape.lv[0], 3] = O.OracleBackend.const(shape.table_size + 5)
+        with pytest.raises(zkgpu.ZkGpuError):
+            pk.prove(adv, pi, 1)
+        # and the library stays usable afterwards
+        adv, pi = circ.witness(2)
+        assert po.verify(pk.prove(adv, pi, 3), pi)
+    finally:
+        pk.release(); params.release()

@@ -96,7 +96,7 @@ def test_constraint_system_sizes(hl, name):
             shape.extended_k, shape.num_evals, shape.proof_len]
     assert [int(x) for x in info] == want
     # proof length formula of the verifier generator (codegen/util.rs:175-186)
-    assert shape.proof_len == 64 * (shape.num_advice + shape.num_perm_sets + 1 + shape.num_quotients) + 32 * shape.num_evals + 128
+    assert shape.proof_len == 64 * (shape.num_advice + 3 * shape.n_lookup + shape.num_perm_sets + 1 + shape.num_quotients) + 32 * shape.num_evals + 128
 
 
 def test_malformed_blobs_rejected(hl):

@@ -29,6 +29,8 @@ struct CsDesc {
     std::vector<fr_t> constants;
     std::vector<std::vector<ExprIns>> gates;
     std::vector<ColRef> perm_columns;
+    struct Lookup { std::vector<std::vector<ExprIns>> inputs, tables; };   // cs.lookups(): input / table expressions
+    std::vector<Lookup> lookups;
     std::vector<fr_t> fixed;  // num_fixed * n, column-major
     std::vector<CopyRef> copies;
     std::vector<uint8_t> blob;
@@ -53,11 +55,19 @@ struct CsDesc {
         }
         return mx;
     }
+    // ConstraintSystem::degree(): permutation 3, lookup max(4, 2 + input_degree + table_degree), gates their own
     unsigned degree() const {
         unsigned d = perm_columns.empty() ? 1 : 3;
+        for (auto& l : lookups) {
+            unsigned di = 1, dt = 1;
+            for (auto& e : l.inputs) di = std::max(di, expr_degree(e));
+            for (auto& e : l.tables) dt = std::max(dt, expr_degree(e));
+            d = std::max(d, std::max(4u, 2 + di + dt));
+        }
         for (auto& g : gates) d = std::max(d, expr_degree(g));
         return d;
     }
+    size_t num_lookups() const { return lookups.size(); }
     unsigned blinding_factors() const {
         std::vector<unsigned> cnt(num_advice, 0);
         for (auto& q : advice_queries) cnt[q.column]++;
@@ -76,9 +86,10 @@ struct CsDesc {
         return ek;
     }
     size_t num_evals() const {
-        return advice_queries.size() + fixed_queries.size() + 1 + perm_columns.size() + (num_perm_sets() ? 3 * num_perm_sets() - 1 : 0);
+        return advice_queries.size() + fixed_queries.size() + 1 + perm_columns.size() + (num_perm_sets() ? 3 * num_perm_sets() - 1 : 0) + 5 * num_lookups();
     }
-    size_t proof_len() const { return 64 * ((size_t)num_advice + num_perm_sets() + 1 + num_quotients()) + 32 * num_evals() + 128; }
+    // codegen/util.rs:175-186: advice | 2L permuted | P + L grand products | random | Q quotient pieces | evals | W, W'
+    size_t proof_len() const { return 64 * ((size_t)num_advice + 3 * num_lookups() + num_perm_sets() + 1 + num_quotients()) + 32 * num_evals() + 128; }
 
     static CsDesc parse(const uint8_t* data, size_t len) {
         CsDesc c;
@@ -94,7 +105,12 @@ struct CsDesc {
         uint32_t ng = u32(); c.gates.resize(ng);
         for (auto& g : c.gates) { uint32_t m = u32(); g.resize(m); for (auto& i : g) { i.op = u32(); i.arg = u32(); } }
         uint32_t np = u32(); c.perm_columns.resize(np); for (auto& pc : c.perm_columns) { pc.type = u32(); pc.index = u32(); }
-        ZK_REQUIRE(u32() == 0, "lookup arguments are not supported yet");
+        auto rexpr = [&](std::vector<ExprIns>& g) { uint32_t m = u32(); ZK_REQUIRE(m <= 4096, "expression too long"); g.resize(m); for (auto& i : g) { i.op = u32(); i.arg = u32(); } };
+        uint32_t nl = u32(); ZK_REQUIRE(nl <= 64, "too many lookups"); c.lookups.resize(nl);
+        for (auto& l : c.lookups) {
+            uint32_t ni = u32(); ZK_REQUIRE(ni >= 1 && ni <= 16, "lookup: bad input expression count"); l.inputs.resize(ni); for (auto& e : l.inputs) rexpr(e);
+            uint32_t nt = u32(); ZK_REQUIRE(nt == ni, "lookup: input/table expression counts differ"); l.tables.resize(nt); for (auto& e : l.tables) rexpr(e);
+        }
         ZK_REQUIRE(c.num_instance == 1, "exactly one instance column is supported (as in Shielder's circuits)");
         size_t n = c.n();
         ZK_REQUIRE((size_t)(end - p) >= (size_t)c.num_fixed * n * 32, "circuit blob: truncated fixed columns");
@@ -107,7 +123,11 @@ struct CsDesc {
         for (auto& q : c.advice_queries) ZK_REQUIRE(q.column < c.num_advice, "advice query out of range");
         for (auto& q : c.fixed_queries) ZK_REQUIRE(q.column < c.num_fixed, "fixed query out of range");
         for (auto& q : c.instance_queries) ZK_REQUIRE(q.column < c.num_instance, "instance query out of range");
-        for (auto& g : c.gates) {
+        std::vector<const std::vector<ExprIns>*> all_exprs;
+        for (auto& g : c.gates) all_exprs.push_back(&g);
+        for (auto& l : c.lookups) { for (auto& e : l.inputs) all_exprs.push_back(&e); for (auto& e : l.tables) all_exprs.push_back(&e); }
+        for (auto* gp : all_exprs) {
+            const std::vector<ExprIns>& g = *gp;
             int depth = 0;
             for (auto& i : g) {
                 switch (i.op) {

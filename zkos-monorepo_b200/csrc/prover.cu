@@ -49,7 +49,7 @@ struct StepTimer {
 // ---------------------------------------------------------------------------------------------
 // SHPLONK query plan: queries in the order of codegen/pcs.rs:60-104, rotation sets as
 // pcs/bdfg21.rs:443-494 builds them (first-seen order of distinct rotation sets).
-// commitment ids: [0,A) advice | P perm z | F fixed | S sigma | h | random
+// commitment ids: [0,A) advice | P perm z | L lookup z | L permuted inputs | L permuted tables | F fixed | S sigma | h | random
 // ---------------------------------------------------------------------------------------------
 struct RotSet {
     std::vector<int> rots, diffs, comms;
@@ -58,17 +58,23 @@ struct RotSet {
 struct QueryPlan {
     std::vector<int> superset;
     std::vector<RotSet> sets;
-    int id_z0 = 0, id_fixed0 = 0, id_sigma0 = 0, id_h = 0, id_random = 0;
+    int id_z0 = 0, id_lz0 = 0, id_la0 = 0, id_ls0 = 0, id_fixed0 = 0, id_sigma0 = 0, id_h = 0, id_random = 0;
     void build(const CsDesc& cs) {
-        const int A = cs.num_advice, P = cs.num_perm_sets(), F = cs.num_fixed, S = (int)cs.perm_columns.size();
-        id_z0 = A; id_fixed0 = A + P; id_sigma0 = A + P + F; id_h = A + P + F + S; id_random = id_h + 1;
+        const int A = cs.num_advice, P = cs.num_perm_sets(), F = cs.num_fixed, S = (int)cs.perm_columns.size(), L = (int)cs.num_lookups();
+        id_z0 = A; id_lz0 = A + P; id_la0 = id_lz0 + L; id_ls0 = id_la0 + L; id_fixed0 = id_ls0 + L; id_sigma0 = id_fixed0 + F;
+        id_h = id_sigma0 + S; id_random = id_h + 1;
         const int e_fix = (int)cs.advice_queries.size(), e_rand = e_fix + (int)cs.fixed_queries.size();
-        const int e_sigma = e_rand + 1, e_z = e_sigma + S, e_h = (int)cs.num_evals();
+        const int e_sigma = e_rand + 1, e_z = e_sigma + S, e_lk = e_z + (P ? 3 * P - 1 : 0), e_h = (int)cs.num_evals();
         struct Q { int comm, rot, eval; };
         std::vector<Q> qs;
         for (size_t i = 0; i < cs.advice_queries.size(); ++i) qs.push_back({(int)cs.advice_queries[i].column, cs.advice_queries[i].rotation, (int)i});
         for (int s = 0; s < P; ++s) { qs.push_back({id_z0 + s, 0, e_z + 3 * s}); qs.push_back({id_z0 + s, 1, e_z + 3 * s + 1}); }
         for (int s = P - 2; s >= 0; --s) qs.push_back({id_z0 + s, cs.rotation_last(), e_z + 3 * s + 2});
+        for (int l = 0; l < L; ++l) {  // codegen/pcs.rs:80-92
+            const int e = e_lk + 5 * l;
+            qs.push_back({id_lz0 + l, 0, e}); qs.push_back({id_la0 + l, 0, e + 2}); qs.push_back({id_ls0 + l, 0, e + 4});
+            qs.push_back({id_la0 + l, -1, e + 3}); qs.push_back({id_lz0 + l, 1, e + 1});
+        }
         for (size_t i = 0; i < cs.fixed_queries.size(); ++i) qs.push_back({id_fixed0 + (int)cs.fixed_queries[i].column, cs.fixed_queries[i].rotation, e_fix + (int)i});
         for (int s = 0; s < S; ++s) qs.push_back({id_sigma0 + s, 0, e_sigma + s});
         qs.push_back({id_h, 0, e_h});
@@ -123,6 +129,9 @@ struct ProverWs {
     DevBuf<fr_t> carries;
     ~ProverWs() { if (stream) cudaStreamDestroy(stream); }
     DevBuf<fr_t> adv, inst, z, randp, adv_ext, z_ext, h, hpoly, comb, hx, lx, tmp1, tmp2, scratch, evals, low;
+    DevBuf<fr_t> lk_in, lk_tab, lk_a, lk_s, lk_z, lk_ext, sort_a, sort_t;   // lookups: [B][L][n] (lk_ext: [B][L][3][en])
+    DevBuf<uint64_t> raw_la, raw_ls, raw_lz;
+    DevBuf<int> d_error;
     DevBuf<uint64_t> raw_adv, raw_z;
     DevBuf<uint8_t> seeds;
     DevBuf<Challenges> ch;
@@ -139,7 +148,8 @@ struct ProverWs {
 struct PkEntry {
     CsDesc cs;
     uint64_t srs_handle = 0;
-    unsigned k = 0, ek = 0, A = 0, F = 0, S = 0, P = 0, Q = 0, bf = 0, chunk = 0;
+    unsigned k = 0, ek = 0, A = 0, F = 0, S = 0, P = 0, Q = 0, bf = 0, chunk = 0, L = 0;
+    DevBuf<uint32_t> lk_prog, lk_expr_off, lk_off;
     size_t n = 0, en = 0, ustart = 0, num_evals = 0, proof_len = 0;
     int rot_last = 0;
     fr_t omega, omega_inv, ext_omega, ext_omega_inv, n_inv, en_inv, zeta, zeta_inv, digest;
@@ -263,6 +273,7 @@ static std::unique_ptr<PkEntry> keygen(Context& C, uint64_t srs_handle, const ui
     pk.srs_handle = srs_handle;
     pk.k = cs.k; pk.n = cs.n(); pk.ek = cs.extended_k(); pk.en = (size_t)1 << pk.ek;
     pk.A = cs.num_advice; pk.F = cs.num_fixed; pk.S = (unsigned)cs.perm_columns.size(); pk.P = cs.num_perm_sets(); pk.Q = cs.num_quotients();
+    pk.L = (unsigned)cs.num_lookups();
     pk.bf = cs.blinding_factors(); pk.chunk = cs.chunk_len(); pk.ustart = cs.unusable_start(); pk.rot_last = cs.rotation_last();
     pk.num_evals = cs.num_evals(); pk.proof_len = cs.proof_len();
     ZK_REQUIRE(pk.ek <= 24, "keygen: extended domain too large");
@@ -360,6 +371,18 @@ static std::unique_ptr<PkEntry> keygen(Context& C, uint64_t srs_handle, const ui
             return v;
         };
         upload(pk.adv_q, qv(cs.advice_queries), st); upload(pk.fix_q, qv(cs.fixed_queries), st); upload(pk.inst_q, qv(cs.instance_queries), st);
+        // lookup expression programs: lookup l owns expressions [lk_off[l], lk_off[l+1]) (inputs, then tables)
+        std::vector<uint32_t> lprog, eoff{0}, loff{0};
+        for (auto& l : cs.lookups) {
+            for (auto* group : {&l.inputs, &l.tables})
+                for (auto& e : *group) {
+                    for (auto& i : e) { lprog.push_back(i.op); lprog.push_back(i.arg); }
+                    eoff.push_back((uint32_t)(lprog.size() / 2));
+                }
+            loff.push_back((uint32_t)(eoff.size() - 1));
+        }
+        if (lprog.empty()) lprog.assign(2, 0);
+        upload(pk.lk_prog, lprog, st); upload(pk.lk_expr_off, eoff, st); upload(pk.lk_off, loff, st);
         ZK_CUDA(cudaStreamSynchronize(st));
     }
     // opaque vk digest (see oracle/plonk.hpp header): keccak(blob ‖ fixed commitments ‖ sigma commitments) mod r
@@ -379,18 +402,25 @@ static std::unique_ptr<PkEntry> keygen(Context& C, uint64_t srs_handle, const ui
 // ---------------------------------------------------------------------------------------------
 struct ProofState {
     Transcript tr;
-    fr_t beta, gamma, y, x, xn, zeta, nu, mu;
+    fr_t theta, beta, gamma, y, x, xn, zeta, nu, mu;
     std::vector<fr_t> evals;                 // num_evals + 1 (quotient eval last)
     std::vector<fr_t> points;                // x * omega^r for r in superset
     std::vector<std::vector<fr_t>> rcomb;    // per set: low-degree remainder coefficients
     explicit ProofState(uint8_t* out) : tr(out) {}
 };
 
+static LookupProgs lookup_progs(const PkEntry& pk) {
+    LookupProgs lp;
+    lp.prog = pk.lk_prog.p; lp.expr_off = pk.lk_expr_off.p; lp.lk_off = pk.lk_off.p; lp.constants = pk.constants.p;
+    lp.adv_q = pk.adv_q.p; lp.fix_q = pk.fix_q.p; lp.inst_q = pk.inst_q.p; lp.L = pk.L;
+    return lp;
+}
+
 static size_t default_batch(const PkEntry& pk) {
     if (const char* e = getenv("ZKGPU_PROVER_BATCH")) { long v = atol(e); if (v > 0) return (size_t)v; }
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    size_t per = ((size_t)(pk.A + 1 + pk.P + 1) * pk.en + (size_t)(pk.A + 2 * pk.P + 8 + 3 * pk.plan.sets.size()) * pk.n) * sizeof(fr_t);
+    size_t per = ((size_t)(pk.A + 1 + pk.P + 1 + 3 * pk.L) * pk.en + (size_t)(pk.A + 2 * pk.P + 7 * pk.L + 8 + 3 * pk.plan.sets.size()) * pk.n) * sizeof(fr_t);
     size_t B = (size_t)(free_b * 0.2) / std::max<size_t>(per, 1);
     return std::max<size_t>(1, std::min<size_t>(B, 128));
 }
@@ -403,12 +433,20 @@ static void ensure_ws(PkEntry& pk, ProverWs& W, size_t B) {
     W.hpoly.ensure(B * n); W.comb.ensure(B * ns * n); W.hx.ensure(B * n); W.lx.ensure(B * n);
     W.tmp1.ensure(B * ns * n); W.tmp2.ensure(B * ns * n);
     W.evals.ensure(B * (pk.num_evals + 1)); W.low.ensure(B * (ns + 1) * 4);
+    if (pk.L) {
+        const size_t BL = B * pk.L;
+        W.lk_in.ensure(BL * n); W.lk_tab.ensure(BL * n); W.lk_a.ensure(BL * n); W.lk_s.ensure(BL * n); W.lk_z.ensure(BL * n);
+        W.sort_a.ensure(BL * n); W.sort_t.ensure(BL * n); W.lk_ext.ensure(BL * 3 * en);
+        W.raw_la.ensure(BL * (pk.bf + 1) * 8); W.raw_ls.ensure(BL * (pk.bf + 1) * 8); W.raw_lz.ensure(BL * pk.bf * 8);
+        W.carries.ensure(BL);
+    }
+    W.d_error.ensure(1);
     W.raw_adv.ensure(std::max<size_t>(1, B * pk.A * (pk.bf + 1) * 8)); W.raw_z.ensure(std::max<size_t>(1, B * pk.P * pk.bf * 8));
     W.seeds.ensure(B * 32); W.ch.ensure(B);
-    size_t max_pts = B * std::max<size_t>(std::max<size_t>(pk.A, pk.P + 1), std::max<size_t>(pk.Q, 1));
+    size_t max_pts = B * std::max<size_t>(std::max<size_t>(pk.A, pk.P + pk.L + 1), std::max<size_t>(pk.Q, 2 * pk.L + 1));
     W.aff.ensure(max_pts);
     W.h_aff.ensure(max_pts * sizeof(g1_affine_t)); W.h_evals.ensure(B * (pk.num_evals + 1) * sizeof(fr_t));
-    ZK_REQUIRE(2 * B * pk.P * n <= B * (pk.A + 1) * en, "workspace aliasing assumption violated");
+    ZK_REQUIRE(2 * B * (pk.P + pk.L) * n <= B * (pk.A + 1) * en, "workspace aliasing assumption violated");
 }
 
 static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* advice, bool advice_on_device, const fr_t* instance, size_t num_pi,
@@ -425,7 +463,9 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
     // ---- step 0: transcripts, RNG streams, uploads ------------------------------------------
     std::vector<ProofState> ps;
     ps.reserve(B);
+    const size_t L = pk.L;
     std::vector<uint64_t> raw_adv(B * A * (bf + 1) * 8), raw_z(B * P * bf * 8);
+    std::vector<uint64_t> raw_la(B * L * (bf + 1) * 8), raw_ls(B * L * (bf + 1) * 8), raw_lz(B * L * bf * 8);
     std::vector<uint8_t> cseeds(B * 32);
     for (size_t b = 0; b < B; ++b) {
         ps.emplace_back(proofs + b * pk.proof_len);
@@ -436,9 +476,20 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
         // advice blinding rows column by column, then one unused Blind per column
         for (size_t t = 0; t < A * (bf + 1); ++t) rng.next_wide(&raw_adv[(b * A * (bf + 1) + t) * 8]);
         for (size_t c = 0; c < A; ++c) rng.skip_wide();
+        // lookups (commit_permuted): blinding rows of the permuted input, of the permuted table, then the two Blinds
+        for (size_t l = 0; l < L; ++l) {
+            for (size_t t = 0; t < bf + 1; ++t) rng.next_wide(&raw_la[((b * L + l) * (bf + 1) + t) * 8]);
+            for (size_t t = 0; t < bf + 1; ++t) rng.next_wide(&raw_ls[((b * L + l) * (bf + 1) + t) * 8]);
+            rng.skip_wide(); rng.skip_wide();
+        }
         // permutation: per set bf blinding rows, then its unused Blind
         for (size_t s = 0; s < P; ++s) {
             for (size_t t = 0; t < bf; ++t) rng.next_wide(&raw_z[((b * P + s) * bf + t) * 8]);
+            rng.skip_wide();
+        }
+        // lookups (commit_product): bf blinding rows of z, then its Blind
+        for (size_t l = 0; l < L; ++l) {
+            for (size_t t = 0; t < bf; ++t) rng.next_wide(&raw_lz[((b * L + l) * bf + t) * 8]);
             rng.skip_wide();
         }
         // vanishing: ChaCha20 seed for the random polynomial, its Blind; quotient piece Blinds follow (unused)
@@ -450,6 +501,7 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
     if (num_pi)
         ZK_CUDA(cudaMemcpy2DAsync(W.inst.p, n * sizeof(fr_t), instance, num_pi * sizeof(fr_t), num_pi * sizeof(fr_t), B, cudaMemcpyHostToDevice, st));
     h2d(W.raw_adv.p, raw_adv, st); h2d(W.raw_z.p, raw_z, st); h2d(W.seeds.p, cseeds, st);
+    if (L) { h2d(W.raw_la.p, raw_la, st); h2d(W.raw_ls.p, raw_ls, st); h2d(W.raw_lz.p, raw_lz, st); ZK_CUDA(cudaMemsetAsync(W.d_error.p, 0, sizeof(int), st)); }
 
     auto fetch_points = [&](size_t count) -> const g1_affine_t* {
         ZK_CUDA(cudaMemcpyAsync(W.h_aff.p, W.aff.p, count * sizeof(g1_affine_t), cudaMemcpyDeviceToHost, st));
@@ -458,7 +510,7 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
     };
     std::vector<Challenges> ch(B);
     auto push_challenges = [&]() {
-        for (size_t b = 0; b < B; ++b) { ch[b].beta = ps[b].beta; ch[b].gamma = ps[b].gamma; ch[b].y = ps[b].y; ch[b].x = ps[b].x; }
+        for (size_t b = 0; b < B; ++b) { ch[b].theta = ps[b].theta; ch[b].beta = ps[b].beta; ch[b].gamma = ps[b].gamma; ch[b].y = ps[b].y; ch[b].x = ps[b].x; }
         h2d(W.ch.p, ch, st);
     };
 
@@ -471,11 +523,32 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
         const g1_affine_t* pts = fetch_points(B * A);
         for (size_t b = 0; b < B; ++b) {
             for (size_t c = 0; c < A; ++c) ps[b].tr.write_point(pts[b * A + c]);
-            (void)ps[b].tr.squeeze();  // theta (no lookups)
-            ps[b].beta = ps[b].tr.squeeze(); ps[b].gamma = ps[b].tr.squeeze();
-            ps[b].y = fr_t::zero(); ps[b].x = fr_t::zero();
+            ps[b].theta = ps[b].tr.squeeze();
+            ps[b].beta = fr_t::zero(); ps[b].gamma = fr_t::zero(); ps[b].y = fr_t::zero(); ps[b].x = fr_t::zero();
         }
     }
+    if (L) {
+        // lookup arguments, part 1: compress with theta, permute the (input, table) pairs, blind, commit
+        push_challenges();
+        LookupCompressArgs la;
+        la.adv = W.adv.p; la.adv_proof_stride = A * n; la.inst = W.inst.p; la.inst_proof_stride = n; la.fixed_vals = pk.fixed_vals.p;
+        la.ch = W.ch.p; la.lp = lookup_progs(pk); la.k = pk.k;
+        launch_lookup_compress(la, W.lk_in.p, W.lk_tab.p, B, st);
+        launch_lookup_permute(W.lk_in.p, W.lk_tab.p, W.lk_a.p, W.lk_s.p, W.sort_a.p, W.sort_t.p, pk.k, pk.ustart, B * L, W.d_error.p, st);
+        launch_scatter_random(W.lk_a.p, L * n, n, pk.ustart, W.raw_la.p, B, L, bf + 1, st);
+        launch_scatter_random(W.lk_s.p, L * n, n, pk.ustart, W.raw_ls.p, B, L, bf + 1, st);
+        trace_dev("lookup_permuted_input", W.lk_a.p, n, L, n, st);
+        trace_dev("lookup_permuted_table", W.lk_s.p, n, L, n, st);
+        commit(C, pk, W, 1, W.lk_a.p, B * L, 0, 0, W.aff.p, st);
+        commit(C, pk, W, 1, W.lk_s.p, B * L, 0, 0, W.aff.p + B * L, st);
+        int err = 0;
+        ZK_CUDA(cudaMemcpyAsync(&err, W.d_error.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        const g1_affine_t* pts = fetch_points(2 * B * L);
+        ZK_REQUIRE(err == 0, "create_proof: a lookup input is not in its table (ConstraintSystemFailure)");
+        for (size_t b = 0; b < B; ++b)
+            for (size_t l = 0; l < L; ++l) { ps[b].tr.write_point(pts[b * L + l]); ps[b].tr.write_point(pts[B * L + b * L + l]); }
+    }
+    for (size_t b = 0; b < B; ++b) { ps[b].beta = ps[b].tr.squeeze(); ps[b].gamma = ps[b].tr.squeeze(); }
     push_challenges();
 
     timer.lap(1);
@@ -497,10 +570,23 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
         trace_dev("z", W.z.p, n, P, n, st);
         commit(C, pk, W, 1, W.z.p, B * P, 0, 0, W.aff.p, st);
     }
+    if (L) {
+        // lookup arguments, part 2: grand products
+        fr_t* num = W.adv_ext.p + 2 * B * P * n; fr_t* den = num + B * L * n;
+        {
+            KtScope kt(KT_PERM, st);
+            launch_lookup_num_den(W.lk_in.p, W.lk_tab.p, W.lk_a.p, W.lk_s.p, W.ch.p, num, den, pk.k, pk.L, B, st);
+            launch_batch_inverse(den, B * L * n, st);
+            launch_perm_scan(num, den, W.lk_z.p, pk.k, B * L, st);
+            launch_perm_finalize(W.lk_z.p, W.carries.p, pk.k, 1, pk.bf, W.raw_lz.p, B * L, st);
+        }
+        trace_dev("lookup_z", W.lk_z.p, n, L, n, st);
+        commit(C, pk, W, 1, W.lk_z.p, B * L, 0, 0, W.aff.p + B * P, st);
+    }
     launch_chacha_poly(W.seeds.p, W.randp.p, n, B, st);
     trace_dev("random_poly", W.randp.p, n, 1, n, st);
-    commit(C, pk, W, 0, W.randp.p, B, 0, 0, W.aff.p + B * P, st);
-    ZK_CUDA(cudaMemcpyAsync(W.h_aff.p, W.aff.p, B * (P + 1) * sizeof(g1_affine_t), cudaMemcpyDeviceToHost, st));
+    commit(C, pk, W, 0, W.randp.p, B, 0, 0, W.aff.p + B * (P + L), st);
+    ZK_CUDA(cudaMemcpyAsync(W.h_aff.p, W.aff.p, B * (P + L + 1) * sizeof(g1_affine_t), cudaMemcpyDeviceToHost, st));
     cudaEvent_t ev_pts;
     ZK_CUDA(cudaEventCreateWithFlags(&ev_pts, cudaEventDisableTiming));
     ZK_CUDA(cudaEventRecord(ev_pts, st));
@@ -508,6 +594,12 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
     if (P) {
         intt_n(pk, W, W.z.p, B * P, st);
         coset_ext(pk, W, W.z.p, W.z_ext.p, B, P, P * en, st);
+    }
+    if (L) {
+        intt_n(pk, W, W.lk_z.p, B * L, st); intt_n(pk, W, W.lk_a.p, B * L, st); intt_n(pk, W, W.lk_s.p, B * L, st);
+        coset_ext(pk, W, W.lk_z.p, W.lk_ext.p, B * L, 1, 3 * en, st);
+        coset_ext(pk, W, W.lk_a.p, W.lk_ext.p + en, B * L, 1, 3 * en, st);
+        coset_ext(pk, W, W.lk_s.p, W.lk_ext.p + 2 * en, B * L, 1, 3 * en, st);
     }
     intt_n(pk, W, W.adv.p, B * A, st);
     intt_n(pk, W, W.inst.p, B, st);
@@ -519,7 +611,8 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
         const g1_affine_t* pts = W.h_aff.as<g1_affine_t>();
         for (size_t b = 0; b < B; ++b) {
             for (size_t s = 0; s < P; ++s) ps[b].tr.write_point(pts[b * P + s]);
-            ps[b].tr.write_point(pts[B * P + b]);
+            for (size_t l = 0; l < L; ++l) ps[b].tr.write_point(pts[B * P + b * L + l]);
+            ps[b].tr.write_point(pts[B * (P + L) + b]);
             ps[b].y = ps[b].tr.squeeze();
         }
     }
@@ -541,6 +634,7 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
         ea.adv_q = pk.adv_q.p; ea.fix_q = pk.fix_q.p; ea.inst_q = pk.inst_q.p;
         ea.num_gates = (unsigned)cs.gates.size(); ea.A = pk.A; ea.S = pk.S; ea.chunk = pk.chunk; ea.P = pk.P; ea.k = pk.k; ea.ek = pk.ek;
         ea.rotation_last = pk.rot_last; ea.zeta = pk.zeta;
+        ea.lk_ext = W.lk_ext.p; ea.lk_ext_proof_stride = 3 * L * en; ea.lp = lookup_progs(pk);
         launch_eval_h(ea, W.h.p, B, st);
     }
     trace_dev("h_evals", W.h.p, en, 1, en, st);
@@ -596,6 +690,14 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
                 j->poly = zp; j->x = at(1); ++j;
                 if (s + 1 < P) { j->poly = zp; j->x = at(pk.rot_last); ++j; }
             }
+            for (size_t l = 0; l < L; ++l) {
+                const fr_t *zp = W.lk_z.p + (b * L + l) * n, *ap = W.lk_a.p + (b * L + l) * n, *sp = W.lk_s.p + (b * L + l) * n;
+                j->poly = zp; j->x = x; ++j;
+                j->poly = zp; j->x = at(1); ++j;
+                j->poly = ap; j->x = x; ++j;
+                j->poly = ap; j->x = at(-1); ++j;
+                j->poly = sp; j->x = x; ++j;
+            }
             j->poly = W.hpoly.p + b * n; j->x = x; ++j;  // quotient evaluation: computed, not written
             ZK_REQUIRE((size_t)(j - &jobs[b * (NE + 1)]) == NE + 1, "internal: evaluation count mismatch");
             p.points.clear();
@@ -620,7 +722,10 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
     // ---- step 5: SHPLONK h(X) -----------------------------------------------------------------
     auto poly_of = [&](size_t b, int id) -> const fr_t* {
         if (id < pk.plan.id_z0) return W.adv.p + (b * A + id) * n;
-        if (id < pk.plan.id_fixed0) return W.z.p + (b * P + (id - pk.plan.id_z0)) * n;
+        if (id < pk.plan.id_lz0) return W.z.p + (b * P + (id - pk.plan.id_z0)) * n;
+        if (id < pk.plan.id_la0) return W.lk_z.p + (b * L + (id - pk.plan.id_lz0)) * n;
+        if (id < pk.plan.id_ls0) return W.lk_a.p + (b * L + (id - pk.plan.id_la0)) * n;
+        if (id < pk.plan.id_fixed0) return W.lk_s.p + (b * L + (id - pk.plan.id_ls0)) * n;
         if (id < pk.plan.id_sigma0) return pk.fixed_polys.p + (size_t)(id - pk.plan.id_fixed0) * n;
         if (id < pk.plan.id_h) return pk.sigma_polys.p + (size_t)(id - pk.plan.id_sigma0) * n;
         return id == pk.plan.id_h ? W.hpoly.p + b * n : W.randp.p + b * n;

@@ -35,6 +35,27 @@ __device__ __forceinline__ fr_t fr_delta() {
     return d;
 }
 
+// postfix expression interpreter shared by the quotient evaluation and the lookup compression
+template <class FF, class FA, class FI>
+__device__ __forceinline__ fr_t run_expr(const uint32_t* prog, uint32_t pc0, uint32_t pc1, const fr_t* constants, FF fixed_at, FA advice_at, FI inst_at) {
+    fr_t stack[8];
+    int sp = 0;
+    for (uint32_t pc = pc0; pc < pc1; ++pc) {
+        uint32_t op = prog[2 * pc], arg = prog[2 * pc + 1];
+        switch (op) {
+            case OP_CONST: stack[sp++] = fe_ldg(constants + arg); break;
+            case OP_FIXED: stack[sp++] = fixed_at(arg); break;
+            case OP_ADVICE: stack[sp++] = advice_at(arg); break;
+            case OP_INSTANCE: stack[sp++] = inst_at(arg); break;
+            case OP_NEG: stack[sp - 1] = neg(stack[sp - 1]); break;
+            case OP_ADD: stack[sp - 2] = stack[sp - 2] + stack[sp - 1]; --sp; break;
+            case OP_MUL: stack[sp - 2] = stack[sp - 2] * stack[sp - 1]; --sp; break;
+            default: stack[sp - 1] = stack[sp - 1] * fe_ldg(constants + arg); break;  // OP_SCALE
+        }
+    }
+    return stack[0];
+}
+
 // ---------------------------------------------------------------------------------------------
 // blinding rows
 // ---------------------------------------------------------------------------------------------
@@ -245,25 +266,12 @@ __global__ void __launch_bounds__(128) k_eval_h(const EvalHArgs a, fr_t* h, size
     const fr_t y = fe_ldg(&a.ch[b].y);
     auto rot = [&](int r) -> size_t { return (i + ((size_t)(long)r << rs)) & (en - 1); };
 
+    auto fixed_at = [&](uint32_t q) { return fe_ldg(a.fixed_ext + (size_t)a.fix_q[2 * q] * en + rot(a.fix_q[2 * q + 1])); };
+    auto advice_at = [&](uint32_t q) { return fe_load(adv + (size_t)a.adv_q[2 * q] * en + rot(a.adv_q[2 * q + 1])); };
+    auto inst_at = [&](uint32_t q) { return fe_load(adv + (size_t)a.A * en + rot(a.inst_q[2 * q + 1])); };
     fr_t v = fr_t::zero();
-    fr_t stack[8];
-    for (unsigned g = 0; g < a.num_gates; ++g) {
-        int sp = 0;
-        for (uint32_t pc = a.gate_off[g]; pc < a.gate_off[g + 1]; ++pc) {
-            uint32_t op = a.prog[2 * pc], arg = a.prog[2 * pc + 1];
-            switch (op) {
-                case OP_CONST: stack[sp++] = fe_ldg(a.constants + arg); break;
-                case OP_FIXED: stack[sp++] = fe_ldg(a.fixed_ext + (size_t)a.fix_q[2 * arg] * en + rot(a.fix_q[2 * arg + 1])); break;
-                case OP_ADVICE: stack[sp++] = fe_load(adv + (size_t)a.adv_q[2 * arg] * en + rot(a.adv_q[2 * arg + 1])); break;
-                case OP_INSTANCE: stack[sp++] = fe_load(adv + (size_t)a.A * en + rot(a.inst_q[2 * arg + 1])); break;
-                case OP_NEG: stack[sp - 1] = neg(stack[sp - 1]); break;
-                case OP_ADD: stack[sp - 2] = stack[sp - 2] + stack[sp - 1]; --sp; break;
-                case OP_MUL: stack[sp - 2] = stack[sp - 2] * stack[sp - 1]; --sp; break;
-                default: stack[sp - 1] = stack[sp - 1] * fe_ldg(a.constants + arg); break;  // OP_SCALE
-            }
-        }
-        v = v * y + stack[0];
-    }
+    for (unsigned g = 0; g < a.num_gates; ++g)
+        v = v * y + run_expr(a.prog, a.gate_off[g], a.gate_off[g + 1], a.constants, fixed_at, advice_at, inst_at);
     if (a.P) {
         const fr_t* z = a.z_ext + b * a.z_ext_proof_stride;
         const fr_t beta = fe_ldg(&a.ch[b].beta), gamma = fe_ldg(&a.ch[b].gamma);
@@ -292,6 +300,30 @@ __global__ void __launch_bounds__(128) k_eval_h(const EvalHArgs a, fr_t* h, size
                 cur = cur * delta;
             }
             v = v * y + (left - right) * lact;
+        }
+    }
+    if (a.lp.L) {
+        const fr_t* lk = a.lk_ext + b * a.lk_ext_proof_stride;
+        const fr_t theta = fe_ldg(&a.ch[b].theta), beta = fe_ldg(&a.ch[b].beta), gamma = fe_ldg(&a.ch[b].gamma);
+        const fr_t l0 = fe_ldg(a.l0 + i), llast = fe_ldg(a.l_last + i), lact = fe_ldg(a.l_active + i), one = fe_one<FrTag>();
+        const size_t r_next = rot(1), r_prev = rot(-1);
+        for (unsigned l = 0; l < a.lp.L; ++l) {
+            const fr_t* zc = lk + (size_t)(3 * l) * en;
+            const fr_t* ac = zc + en;
+            const fr_t* sc = ac + en;
+            const uint32_t e0 = a.lp.lk_off[l], e1 = a.lp.lk_off[l + 1], em = e0 + (e1 - e0) / 2;
+            fr_t cin = fr_t::zero(), ctab = fr_t::zero();
+            for (uint32_t e = e0; e < em; ++e)
+                cin = cin * theta + run_expr(a.lp.prog, a.lp.expr_off[e], a.lp.expr_off[e + 1], a.lp.constants, fixed_at, advice_at, inst_at);
+            for (uint32_t e = em; e < e1; ++e)
+                ctab = ctab * theta + run_expr(a.lp.prog, a.lp.expr_off[e], a.lp.expr_off[e + 1], a.lp.constants, fixed_at, advice_at, inst_at);
+            const fr_t z = fe_load(zc + i), pa = fe_load(ac + i), ps = fe_load(sc + i);
+            const fr_t a_minus_s = pa - ps;
+            v = v * y + (one - z) * l0;
+            v = v * y + (sqr(z) - z) * llast;
+            v = v * y + (fe_load(zc + r_next) * ((pa + beta) * (ps + gamma)) - z * ((cin + beta) * (ctab + gamma))) * lact;
+            v = v * y + a_minus_s * l0;
+            v = v * y + (a_minus_s * (pa - fe_load(ac + r_prev))) * lact;
         }
     }
     v = v * fe_ldg(a.t_inv + (i & (((size_t)1 << rs) - 1)));

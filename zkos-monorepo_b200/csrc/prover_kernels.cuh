@@ -9,7 +9,7 @@ namespace zk {
 struct ColSrc { uint32_t type, index; };  // COL_ADVICE / COL_FIXED / COL_INSTANCE
 
 // Per-proof Fiat-Shamir challenges (Montgomery), device resident: [B] of this struct
-struct Challenges { fr_t beta, gamma, y, x; };
+struct Challenges { fr_t theta, beta, gamma, y, x; };
 
 // dst[b*proof_stride + col*col_stride + row_start + j] = from_u512(raw[(b*cols + col)*rows + j])
 void launch_scatter_random(fr_t* dst, size_t proof_stride, size_t col_stride, size_t row_start, const uint64_t* raw_wide,
@@ -38,6 +38,33 @@ void launch_perm_finalize(fr_t* z, fr_t* carries /*[B][P] scratch*/, unsigned k,
 // random polynomial of the vanishing argument: coefficient i of proof b = Fr::random of ChaCha20(seed_b) block i
 void launch_chacha_poly(const uint8_t* seeds /*[B][32]*/, fr_t* out /*[B][n]*/, size_t n, size_t B, cudaStream_t st);
 
+// ---- lookup arguments (halo2 lookup/prover.rs) ------------------------------------------------------------
+// Expression programs of all lookups, flattened: lookup l owns expressions [lk_off[l], lk_off[l+1]) — first half
+// inputs, second half tables — and expression e owns instructions [expr_off[e], expr_off[e+1]) of `prog`.
+struct LookupProgs {
+    const uint32_t* prog; const uint32_t* expr_off; const uint32_t* lk_off;
+    const fr_t* constants; const int32_t* adv_q; const int32_t* fix_q; const int32_t* inst_q;
+    unsigned L;
+};
+struct LookupCompressArgs {
+    const fr_t* adv; size_t adv_proof_stride;    // [B][A][n] Lagrange values (blinded)
+    const fr_t* inst; size_t inst_proof_stride;  // [B][n]
+    const fr_t* fixed_vals;                      // [F][n]
+    const Challenges* ch;
+    LookupProgs lp;
+    unsigned k;
+};
+// compressed input / table values: out_in, out_tab [B][L][n]
+void launch_lookup_compress(const LookupCompressArgs& a, fr_t* out_in, fr_t* out_tab, size_t B, cudaStream_t st);
+// permute_expression_pair for B*L (input, table) pairs: sorts canonical values (rows < usable), assigns the table
+// column; perm_in / perm_tab [B*L][n] receive rows < usable (blinding rows are written separately).
+// sort_a / sort_t: scratch [B*L][n].  *d_error is set to 1 if an input value is missing from its table.
+void launch_lookup_permute(const fr_t* comp_in, const fr_t* comp_tab, fr_t* perm_in, fr_t* perm_tab, fr_t* sort_a, fr_t* sort_t,
+                           unsigned k, size_t usable, size_t BL, int* d_error, cudaStream_t st);
+// num = (in + beta)(tab + gamma), den = (perm_in + beta)(perm_tab + gamma); all [B][L][n]
+void launch_lookup_num_den(const fr_t* comp_in, const fr_t* comp_tab, const fr_t* perm_in, const fr_t* perm_tab, const Challenges* ch,
+                           fr_t* num, fr_t* den, unsigned k, unsigned L, size_t B, cudaStream_t st);
+
 struct EvalHArgs {
     // per-proof extended cosets
     const fr_t* adv_ext; size_t adv_ext_proof_stride;  // [B][A+1][en], instance coset at column A
@@ -58,6 +85,9 @@ struct EvalHArgs {
     const int32_t* adv_q;  // [num_advice_queries][2] = (column, rotation)
     const int32_t* fix_q;
     const int32_t* inst_q;
+    // lookups: extended cosets [B][L][3][en] in the order (z, permuted input, permuted table)
+    const fr_t* lk_ext; size_t lk_ext_proof_stride;
+    LookupProgs lp;
     unsigned num_gates, A, S, chunk, P, k, ek;
     int rotation_last;
     fr_t zeta;  // coset generator (Montgomery)
