@@ -138,3 +138,18 @@ def test_permutation_assembly(hl):
         touched.add(lc * n + lr); touched.add(rc * n + rr)
     free = np.array([i for i in range(S * n) if i not in touched])
     assert np.array_equal(nxt[free], free)
+
+
+@pytest.mark.parametrize("field,p", [(0, P.R_MOD), (1, P.Q_MOD)])
+def test_binary_inversion(hl, field, p):
+    """fe_inv (binary extended Euclid) == a^(p-2) == big-int inverse, in Montgomery form; 0 -> 0."""
+    rng = np.random.default_rng(5 + field)
+    vals = [0, 1, 2, p - 1, p - 2, (p + 1) // 2, 1 << 253, (1 << 32) - 1] + [int.from_bytes(rng.bytes(40), "little") % p for _ in range(300)]
+    mont = P.int_to_limbs([v * P.MONT_R % p for v in vals])
+    a32 = mont.view(np.uint32)
+    got = np.empty_like(a32); ref = np.empty_like(a32)
+    hl.hl_inv(field, 0, a32.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), C.c_size_t(len(vals)))
+    hl.hl_inv(field, 1, a32.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p), C.c_size_t(len(vals)))
+    assert np.array_equal(got, ref)
+    want = [(pow(v, -1, p) * P.MONT_R % p) if v else 0 for v in vals]
+    assert P.limbs_to_int(got.view(np.uint64)) == want

@@ -106,9 +106,70 @@ __host__ __device__ inline Fe<Tag> fe_pow(const Fe<Tag>& a, const uint32_t* e) {
     return acc;
 }
 template <class Tag>
-__host__ __device__ inline Fe<Tag> fe_inv(const Fe<Tag>& a) {  // a^(p-2); 0 -> 0
+__host__ __device__ inline Fe<Tag> fe_inv_pow(const Fe<Tag>& a) {  // a^(p-2); 0 -> 0
     Fe<Tag> e; fe_set_modm2(e);
     return fe_pow(a, e.l);
+}
+
+// ---- inversion by the binary extended Euclidean algorithm -------------------------------------------------
+// ~2*254 iterations of shifts / conditional subtractions on plain 256-bit integers instead of ~380 dependent
+// Montgomery products: about 6x shorter on the latency-critical single-thread paths (point normalisation, batch
+// inversion seeds).  Input and output in Montgomery form; 0 -> 0.  Same value as a^(p-2) (checked in the tests).
+namespace bininv {
+__host__ __device__ __forceinline__ bool is_even(const uint32_t* x) { return (x[0] & 1u) == 0; }
+__host__ __device__ __forceinline__ bool is_one(const uint32_t* x) { return x[0] == 1u && (x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7]) == 0; }
+__host__ __device__ __forceinline__ bool geq(const uint32_t* x, const uint32_t* y) {
+    for (int i = 7; i >= 0; --i) if (x[i] != y[i]) return x[i] > y[i];
+    return true;
+}
+__host__ __device__ __forceinline__ uint32_t add_n(uint32_t* r, const uint32_t* x, const uint32_t* y) {   // returns carry
+    uint64_t c = 0;
+    for (int i = 0; i < 8; ++i) { c += (uint64_t)x[i] + y[i]; r[i] = (uint32_t)c; c >>= 32; }
+    return (uint32_t)c;
+}
+__host__ __device__ __forceinline__ void sub_n(uint32_t* r, const uint32_t* x, const uint32_t* y) {
+    uint64_t b = 0;
+    for (int i = 0; i < 8; ++i) { uint64_t d = (uint64_t)x[i] - y[i] - b; r[i] = (uint32_t)d; b = (d >> 63) & 1; }
+}
+__host__ __device__ __forceinline__ void shr1(uint32_t* x, uint32_t top) {
+    for (int i = 0; i < 7; ++i) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+    x[7] = (x[7] >> 1) | (top << 31);
+}
+// x <- x / 2 mod p (p odd)
+__host__ __device__ __forceinline__ void half_mod(uint32_t* x, const uint32_t* p) {
+    uint32_t top = 0;
+    if (!is_even(x)) top = add_n(x, x, p);
+    shr1(x, top);
+}
+}  // namespace bininv
+
+template <class Tag>
+__host__ __device__ inline Fe<Tag> fe_inv(const Fe<Tag>& a) {
+    if (a.is_zero()) return a;
+    Fe<Tag> pm2; fe_set_modm2(pm2);
+    uint32_t p[8];
+    for (int i = 0; i < 8; ++i) p[i] = pm2.l[i];
+    p[0] += 2;   // the moduli end in ...01 / ...47: no carry out of the low limb
+    uint32_t u[8], v[8], x1[8], x2[8];
+    for (int i = 0; i < 8; ++i) { u[i] = a.l[i]; v[i] = p[i]; x1[i] = 0; x2[i] = 0; }
+    x1[0] = 1;
+    // invariant: x1 * a == u, x2 * a == v (mod p) with a = the input integer (aR)
+    while (!bininv::is_one(u) && !bininv::is_one(v)) {
+        while (bininv::is_even(u)) { bininv::shr1(u, 0); bininv::half_mod(x1, p); }
+        while (bininv::is_even(v)) { bininv::shr1(v, 0); bininv::half_mod(x2, p); }
+        if (bininv::geq(u, v)) {
+            bininv::sub_n(u, u, v);
+            if (bininv::geq(x1, x2)) bininv::sub_n(x1, x1, x2); else { uint32_t t[8]; bininv::sub_n(t, x2, x1); bininv::sub_n(x1, p, t); }
+        } else {
+            bininv::sub_n(v, v, u);
+            if (bininv::geq(x2, x1)) bininv::sub_n(x2, x2, x1); else { uint32_t t[8]; bininv::sub_n(t, x1, x2); bininv::sub_n(x2, p, t); }
+        }
+    }
+    Fe<Tag> r;   // (aR)^-1 as a plain integer
+    for (int i = 0; i < 8; ++i) r.l[i] = bininv::is_one(u) ? x1[i] : x2[i];
+    // (aR)^-1 * R^3 / R = a^-1 * R: back in Montgomery form
+    Fe<Tag> r2 = fe_r2<Tag>();
+    return r * (r2 * r2);
 }
 
 // 128-bit vector loads/stores (two per element)

@@ -205,11 +205,52 @@ __global__ void __launch_bounds__(128) k_msm_heavy(const g1_affine_t* __restrict
     }
 }
 
+// Latency variant for small batches (single proofs): ZK_SPLIT threads share one bucket, each accumulating a strided
+// slice of the run, then fold through shared memory — 8x shorter dependency chains, more CTAs in flight.
+#define ZK_SPLIT 8
+__global__ void __launch_bounds__(128) k_msm_buckets_split(const g1_affine_t* __restrict__ bases, const uint32_t* __restrict__ offsets,
+                                                           const uint32_t* __restrict__ entries, MsmDims D, size_t M,
+                                                           g1_xyzz_t* __restrict__ buckets, uint32_t* __restrict__ heavy_count,
+                                                           uint64_t* __restrict__ heavy_list) {
+    __shared__ g1_xyzz_t part[128];
+    const size_t K = (size_t)D.G * D.nb;
+    const unsigned lane = threadIdx.x % ZK_SPLIT;
+    size_t idx = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / ZK_SPLIT;
+    const bool live = idx < M * K;
+    g1_xyzz_t acc = g1_xyzz_t::identity();
+    bool heavy = false;
+    if (live) {
+        size_t m = idx / K, key = idx - m * K;
+        const uint32_t* om = offsets + m * (K + 1);
+        const uint32_t* em = entries + m * ((size_t)D.n * D.W);
+        uint32_t b = om[key], e = om[key + 1];
+        heavy = e - b > D.heavy;
+        if (heavy) { if (lane == 0) heavy_list[atomicAdd(heavy_count, 1u)] = idx; }
+        else
+            for (uint32_t t = b + lane; t < e; t += ZK_SPLIT) {
+                uint32_t ref = em[t];
+                const g1_affine_t* p = bases + (ref & 0x7fffffffu);
+                g1_affine_t q;
+                q.x = fe_ldg(&p->x); q.y = fe_ldg(&p->y);
+                xyzz_madd(acc, q, (ref >> 31) != 0);
+            }
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (unsigned s = ZK_SPLIT >> 1; s > 0; s >>= 1) {
+        if (lane < s) part[threadIdx.x] = xyzz_add(part[threadIdx.x], part[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (live && !heavy && lane == 0) xyzz_store(buckets + idx, part[threadIdx.x]);
+}
+
 // block per (m, g); T = blockDim.x threads, each owns L = nb/T consecutive buckets
 #define ZK_REDUCE_T 128
-__global__ void __launch_bounds__(ZK_REDUCE_T) k_msm_reduce(const g1_xyzz_t* __restrict__ buckets, MsmDims D,
-                                                            g1_xyzz_t* __restrict__ groups) {
-    __shared__ g1_xyzz_t part[ZK_REDUCE_T];
+#define ZK_REDUCE_T_LAT 512   // few MSMs in flight: more, shorter segments per bucket group
+__global__ void __launch_bounds__(ZK_REDUCE_T_LAT) k_msm_reduce(const g1_xyzz_t* __restrict__ buckets, MsmDims D,
+                                                                g1_xyzz_t* __restrict__ groups) {
+    extern __shared__ uint4 reduce_smem[];
+    g1_xyzz_t* part = reinterpret_cast<g1_xyzz_t*>(reduce_smem);
     const unsigned T = blockDim.x;
     const unsigned L = D.nb / T;  // host guarantees T | nb
     const g1_xyzz_t* B = buckets + (size_t)blockIdx.x * D.nb;
@@ -332,14 +373,21 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
     {
         KtScope kt(KT_MSM_BUCKETS, st);
         ZK_CUDA(cudaMemsetAsync(ws.heavy_count.p, 0, sizeof(uint32_t), st));
-        ZK_LAUNCH(k_msm_buckets, ceil_div(M * K, 128), 128, 0, st, d_bases, ws.offsets.p, ws.entries.p, D, M, ws.buckets.p,
-                  ws.order.p, ws.heavy_count.p, ws.heavy_list.p);
+        if (M * K < (size_t)148 * 2048)   // latency regime: too few buckets to fill the GPU with one thread each
+            ZK_LAUNCH(k_msm_buckets_split, ceil_div(M * K * ZK_SPLIT, 128), 128, 0, st, d_bases, ws.offsets.p, ws.entries.p, D, M, ws.buckets.p,
+                      ws.heavy_count.p, ws.heavy_list.p);
+        else
+            ZK_LAUNCH(k_msm_buckets, ceil_div(M * K, 128), 128, 0, st, d_bases, ws.offsets.p, ws.entries.p, D, M, ws.buckets.p,
+                      ws.order.p, ws.heavy_count.p, ws.heavy_list.p);
         ZK_LAUNCH(k_msm_heavy, 148 * 8, 128, 0, st, d_bases, ws.offsets.p, ws.entries.p, D, ws.buckets.p, ws.heavy_count.p, ws.heavy_list.p);
     }
     KtScope kt(KT_MSM_REDUCE, st);
-    unsigned T = plan.nb < ZK_REDUCE_T ? plan.nb : ZK_REDUCE_T;
+    unsigned Tmax = M * plan.G < 148 * 4 ? ZK_REDUCE_T_LAT : ZK_REDUCE_T;
+    unsigned T = plan.nb < Tmax ? plan.nb : Tmax;
     g1_xyzz_t* groups = plan.precomp ? d_out : ws.groups.p;
-    ZK_LAUNCH(k_msm_reduce, (unsigned)(M * plan.G), T, 0, st, ws.buckets.p, D, groups);
+    static bool reduce_attr = false;
+    if (!reduce_attr) { ZK_CUDA(cudaFuncSetAttribute(k_msm_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, ZK_REDUCE_T_LAT * (int)sizeof(g1_xyzz_t))); reduce_attr = true; }
+    ZK_LAUNCH(k_msm_reduce, (unsigned)(M * plan.G), T, T * sizeof(g1_xyzz_t), st, ws.buckets.p, D, groups);
     if (!plan.precomp) {
         ZK_LAUNCH(k_msm_combine, ceil_div(M, 64), 64, 0, st, ws.groups.p, D, M, d_out);
     }
