@@ -252,11 +252,13 @@ def main():
     except Exception:
         pass
     hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-    imad = {}
+    imad, traffic = {}, {}
     try:
         imad = json.load(open(os.path.join(ROOT, "profiles", "imad_peak.json")))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")))   # ncu --set full, per launch
     except Exception:
         pass
+    tr_of = lambda kname: (traffic[kname]["dram_bytes_read"] + traffic[kname]["dram_bytes_write"]) if kname in traffic else None
     # algorithmic work per step (DESIGN.md "Kernels"): fixed-base MSM = n*W mixed additions of 10 Fq muls;
     # NTT = 64 bytes per point per transform (32 B for zero-padded inputs)
     W_win, c_win = 254 // 13 + 1, 13
@@ -269,13 +271,14 @@ def main():
     dom = max(ktimes, key=lambda k_: ktimes[k_][0])
     fmul_peak = imad.get("imad_wide_Gops", 11360.0) / 136.0     # Montgomery product = 136 32x32->64 multiply-adds
     roof_imad = {"kernel": "k_msm_buckets", "bound": "imad", "achieved": fmul_bucket / (ktimes["msm_bucket_accumulate"][0] / 1e3) / 1e9 if ktimes["msm_bucket_accumulate"][0] else None,
-                 "peak": fmul_peak, "unit": "Gfieldmul/s", "traffic": None,
+                 "peak": fmul_peak, "unit": "Gfieldmul/s", "traffic": tr_of("k_msm_buckets"),
+                 "traffic_note": "DRAM bytes of one 1024-MSM launch (ncu --set full, profiles/r01_kernel_traffic.json); algorithmic bytes of that launch: 1.24e9",
                  "peak_source": "IMAD.WIDE issue rate measured with tools/imad_peak.cu on this pool / 136 multiply-adds per 254-bit Montgomery product",
                  "launches": ktimes["msm_bucket_accumulate"][1], "ms_total": ktimes["msm_bucket_accumulate"][0],
                  "share_of_kernel_time": ktimes["msm_bucket_accumulate"][0] / total_k_ms}
     roof_imad["frac"] = roof_imad["achieved"] / roof_imad["peak"] if roof_imad["achieved"] else None
     roof_hbm = {"kernel": "k_ntt_tile", "bound": "hbm", "achieved": ntt_bytes / (ktimes["ntt_tile"][0] / 1e3) / 1e9 if ktimes["ntt_tile"][0] else None,
-                "peak": hbm_peak, "unit": "GB/s", "traffic": None, "peak_source": hbm_src,
+                "peak": hbm_peak, "unit": "GB/s", "traffic": tr_of("k_ntt_tile"), "peak_source": hbm_src,
                 "launches": ktimes["ntt_tile"][1], "ms_total": ktimes["ntt_tile"][0], "share_of_kernel_time": ktimes["ntt_tile"][0] / total_k_ms}
     roof_hbm["frac"] = roof_hbm["achieved"] / roof_hbm["peak"] if roof_hbm["achieved"] else None
     roofline = dict(roof_hbm if dom == "ntt_tile" else roof_imad)
