@@ -15,11 +15,19 @@ ROOT = O.ROOT
 CSRC = os.path.join(ROOT, "zkos-monorepo_b200", "csrc")
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    subprocess.check_call(["python3", os.path.join(CSRC, "gen_fp.py")])
-    so = str(tmp_path_factory.mktemp("emu") / "libfpemu.so")
-    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-I", CSRC,
+@pytest.fixture(scope="module", params=["schoolbook", "karatsuba"])
+def emu(request, tmp_path_factory):
+    """schoolbook = the shipped interleaved product (regenerated in place and required to be unchanged);
+    karatsuba = the optional ZK_FP_KARATSUBA=1 variant, generated into a scratch directory."""
+    d = tmp_path_factory.mktemp("emu_" + request.param)
+    if request.param == "schoolbook":
+        shipped = open(os.path.join(CSRC, "fp_gen.inc")).read()
+        subprocess.check_call(["python3", os.path.join(CSRC, "gen_fp.py"), str(d / "fp_gen.inc")], env=dict(os.environ, ZK_FP_KARATSUBA="0"))
+        assert open(str(d / "fp_gen.inc")).read() == shipped, "csrc/fp_gen.inc is stale: run gen_fp.py"
+    else:
+        subprocess.check_call(["python3", os.path.join(CSRC, "gen_fp.py"), str(d / "fp_gen.inc")], env=dict(os.environ, ZK_FP_KARATSUBA="1"))
+    so = str(d / "libfpemu.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-I", str(d), "-I", CSRC,
                            os.path.join(ROOT, "tests", "emu", "fp_emu.cpp"), "-o", so])
     return C.CDLL(so)
 
@@ -36,7 +44,8 @@ def run(emu, field, op, a, b=None):
 @pytest.mark.parametrize("field,p", [(0, P.R_MOD), (1, P.Q_MOD)])
 def test_limb_arithmetic_matches_oracle(emu, field, p):
     rng = np.random.default_rng(7 + field)
-    edge = [0, 1, 2, p - 1, p - 2, (1 << 253) - 1, (1 << 253), (1 << 32) - 1, (1 << 64) - 1, 0xFFFFFFFF << 224 | 5]
+    edge = [0, 1, 2, p - 1, p - 2, (1 << 253) - 1, (1 << 253), (1 << 32) - 1, (1 << 64) - 1, 0xFFFFFFFF << 224 | 5,
+            (1 << 128) - 1, 1 << 128, ((1 << 125) << 128) | (1 << 125), ((1 << 128) - 1) << 120, (3 << 128) | 7, (7 << 128) | 3]
     edge = [e % p for e in edge]
     vals_a = edge * len(edge) + [int.from_bytes(rng.bytes(40), "little") % p for _ in range(20000)]
     vals_b = [e for e in edge for _ in edge] + [int.from_bytes(rng.bytes(40), "little") % p for _ in range(20000)]
