@@ -231,3 +231,26 @@ def test_lookup_circuits_match_oracle(name, k, count):
         assert po.verify(pk.prove(adv, pi, 3), pi)
     finally:
         pk.release(); params.release()
+
+
+def test_coalesced_single_proof_requests(tiny):
+    """Concurrent per-request `prove` calls (the reference hosts' call shape) served through the coalescer:
+    every caller gets the proof the oracle produces for its own witness and seed."""
+    import threading
+    from zkgpu.coalescer import ProofCoalescer
+    shape, circ, po, params, pk = tiny
+    co = ProofCoalescer(pk.prove_batch, max_batch=8, max_wait_ms=20)
+    wits = {i: circ.witness(30 + i) for i in range(12)}
+    got = {}
+
+    def client(i):
+        got[i] = co.prove(wits[i][0], wits[i][1], 900 + i)
+    ts = [threading.Thread(target=client, args=(i,)) for i in wits]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    co.close()
+    assert len(co.batches) < 12
+    for i, (adv, pi) in wits.items():
+        assert got[i] == po.prove(adv, pi, seed=900 + i)
