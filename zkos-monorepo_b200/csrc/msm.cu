@@ -97,6 +97,65 @@ __global__ void k_msm_scatter(const fr_t* __restrict__ scalars, size_t total, Ms
     });
 }
 
+// Single-kernel digit sort for MSMs whose bucket table fits in shared memory (the prover's fixed-base MSMs: 4096
+// buckets): one CTA per MSM histograms the signed digits, scans, and scatters with SHARED-memory atomics; it also
+// emits the bucket order by decreasing run length.  Replaces k_msm_count + k_msm_scan + k_msm_scatter + k_msm_order
+// and their global atomics (the scalars are read twice, from L2).
+__global__ void __launch_bounds__(1024) k_msm_sort_smem(const fr_t* __restrict__ scalars, MsmDims D, uint32_t* __restrict__ offsets,
+                                                        uint32_t* __restrict__ entries, uint32_t* __restrict__ order) {
+    extern __shared__ uint32_t sm_sort[];
+    const unsigned K = D.G * D.nb, T = blockDim.x;
+    uint32_t* cnt = sm_sort;              // [K]    histogram -> cursors
+    uint32_t* part = sm_sort + K;         // [T]
+    uint32_t* hist = part + T;            // [heavy + 2] run-length histogram for the ordering
+    const size_t m = blockIdx.x;
+    const fr_t* sc = scalars + (m / D.inner) * D.outer_stride + (m % D.inner) * D.n;
+    uint32_t* om = offsets + m * ((size_t)K + 1);
+    uint32_t* em = entries + m * ((size_t)D.n * D.W);
+    uint32_t* ord = order + m * (size_t)K;
+    for (unsigned i = threadIdx.x; i < K; i += T) cnt[i] = 0;
+    for (unsigned i = threadIdx.x; i < D.heavy + 2; i += T) hist[i] = 0;
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < D.n; i += T) {
+        fr_t s = from_mont(fe_load(sc + i));
+        for_each_digit(s.l, D.c, D.W, [&](unsigned w, uint32_t mag, bool) { atomicAdd(&cnt[(D.precomp ? 0 : w) * D.nb + (mag - 1)], 1u); });
+    }
+    __syncthreads();
+    // run-length histogram, then exclusive scan of the counts (in place) -> offsets
+    const unsigned per = (K + T - 1) / T, lo = threadIdx.x * per, hi = lo + per < K ? lo + per : K;
+    uint32_t sum = 0;
+    for (unsigned i = lo; i < hi; ++i) { uint32_t c = cnt[i]; sum += c; atomicAdd(&hist[c > D.heavy ? D.heavy + 1 : c], 1u); }
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (unsigned d = 1; d < T; d <<= 1) {
+        uint32_t v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {   // descending exclusive scan of the run-length histogram
+        uint32_t pos = 0;
+        for (int sz = (int)D.heavy + 1; sz >= 0; --sz) { uint32_t c = hist[sz]; hist[sz] = pos; pos += c; }
+    }
+    uint32_t run = part[threadIdx.x] - sum;
+    __syncthreads();
+    for (unsigned i = lo; i < hi; ++i) {
+        uint32_t c = cnt[i];
+        ord[atomicAdd(&hist[c > D.heavy ? D.heavy + 1 : c], 1u)] = i;
+        om[i] = run; cnt[i] = run; run += c;
+    }
+    if (threadIdx.x == T - 1) om[K] = part[T - 1];
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < D.n; i += T) {
+        fr_t s = from_mont(fe_load(sc + i));
+        for_each_digit(s.l, D.c, D.W, [&](unsigned w, uint32_t mag, bool negative) {
+            uint32_t pos = atomicAdd(&cnt[(D.precomp ? 0 : w) * D.nb + (mag - 1)], 1u);
+            uint32_t ref = D.precomp ? w * D.tstride + i : i;
+            em[pos] = ref | (negative ? 0x80000000u : 0u);
+        });
+    }
+}
+
 // Buckets of one MSM ordered by decreasing run length (counting sort on the length, one CTA per MSM), so the
 // 32 lanes of a warp in k_msm_buckets walk runs of (nearly) equal length instead of idling behind the longest.
 #define ZK_HEAVY_MIN 192
@@ -361,7 +420,13 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
     const size_t K = plan.K();
     const size_t total = M * plan.n;
     ZK_REQUIRE(K <= (1u << 30), "msm: too many buckets");
-    {
+    const size_t sort_smem = (K + 1024 + D.heavy + 2) * sizeof(uint32_t);
+    if (K <= 8192 && plan.n <= (1u << 20)) {
+        KtScope kt(KT_MSM_SORT, st);
+        static bool sort_attr = false;
+        if (!sort_attr) { ZK_CUDA(cudaFuncSetAttribute(k_msm_sort_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); sort_attr = true; }
+        ZK_LAUNCH(k_msm_sort_smem, (unsigned)M, 1024, sort_smem, st, d_scalars, D, ws.offsets.p, ws.entries.p, ws.order.p);
+    } else {
         KtScope kt(KT_MSM_SORT, st);
         ZK_LAUNCH(k_msm_count, ceil_div(total, 256), 256, 0, st, d_scalars, total, D, ws.counts.p);
         unsigned scan_threads = K >= 1024 ? 1024 : 32;
