@@ -7,6 +7,7 @@
 //   k_lookup_num_den  : factors of the lookup grand product
 #include "prover_kernels.cuh"
 #include "plonk_types.hpp"
+#include <mutex>
 
 namespace zk {
 
@@ -171,11 +172,8 @@ void launch_lookup_permute(const fr_t* comp_in, const fr_t* comp_tab, fr_t* perm
     unsigned threads = n / 2 < 1024 ? (n / 2 < 32 ? 32 : n / 2) : 1024;
     ZK_LAUNCH(k_lookup_sort, (unsigned)(2 * BL), threads, 0, st, comp_in, comp_tab, sort_a, sort_t, k, (unsigned)usable, BL);
     size_t smem = ((size_t)2 * n + threads) * sizeof(uint32_t);
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
-        ZK_CUDA(cudaFuncSetAttribute(k_lookup_permute, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    static std::once_flag attr_once;   // two pipeline workers may arrive here together
+    std::call_once(attr_once, [] { ZK_CUDA(cudaFuncSetAttribute(k_lookup_permute, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); });
     ZK_LAUNCH(k_lookup_permute, (unsigned)BL, threads, smem, st, sort_a, sort_t, perm_in, perm_tab, k, (unsigned)usable, d_error);
 }
 

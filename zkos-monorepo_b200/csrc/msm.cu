@@ -16,6 +16,7 @@
 // The group sum is independent of accumulation order and every exceptional case of the addition
 // formulas is handled, so the affine-normalised result is bit-exact against the CPU oracle.
 #include "msm.cuh"
+#include <mutex>
 
 namespace zk {
 
@@ -423,8 +424,8 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
     const size_t sort_smem = (K + 1024 + D.heavy + 2) * sizeof(uint32_t);
     if (K <= 8192 && plan.n <= (1u << 20)) {
         KtScope kt(KT_MSM_SORT, st);
-        static bool sort_attr = false;
-        if (!sort_attr) { ZK_CUDA(cudaFuncSetAttribute(k_msm_sort_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); sort_attr = true; }
+        static std::once_flag sort_once;
+        std::call_once(sort_once, [] { ZK_CUDA(cudaFuncSetAttribute(k_msm_sort_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); });
         ZK_LAUNCH(k_msm_sort_smem, (unsigned)M, 1024, sort_smem, st, d_scalars, D, ws.offsets.p, ws.entries.p, ws.order.p);
     } else {
         KtScope kt(KT_MSM_SORT, st);
@@ -450,8 +451,8 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
     unsigned Tmax = M * plan.G < 148 * 4 ? ZK_REDUCE_T_LAT : ZK_REDUCE_T;
     unsigned T = plan.nb < Tmax ? plan.nb : Tmax;
     g1_xyzz_t* groups = plan.precomp ? d_out : ws.groups.p;
-    static bool reduce_attr = false;
-    if (!reduce_attr) { ZK_CUDA(cudaFuncSetAttribute(k_msm_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, ZK_REDUCE_T_LAT * (int)sizeof(g1_xyzz_t))); reduce_attr = true; }
+    static std::once_flag reduce_once;
+    std::call_once(reduce_once, [] { ZK_CUDA(cudaFuncSetAttribute(k_msm_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, ZK_REDUCE_T_LAT * (int)sizeof(g1_xyzz_t))); });
     ZK_LAUNCH(k_msm_reduce, (unsigned)(M * plan.G), T, T * sizeof(g1_xyzz_t), st, ws.buckets.p, D, groups);
     if (!plan.precomp) {
         ZK_LAUNCH(k_msm_combine, ceil_div(M, 64), 64, 0, st, ws.groups.p, D, M, d_out);

@@ -37,11 +37,12 @@ typedef void (*trace_fn)(const char* name, const void* data, size_t bytes);
 static trace_fn g_trace = nullptr;
 // wall-clock seconds spent in each step of prove_sub_batch (every step ends in a stream sync)
 static double g_step_s[8] = {0};
+static std::mutex g_step_mu;   // two pipeline workers accumulate here
 struct StepTimer {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     void lap(int step) {
         auto t1 = std::chrono::steady_clock::now();
-        g_step_s[step] += std::chrono::duration<double>(t1 - t0).count();
+        { std::lock_guard<std::mutex> lk(g_step_mu); g_step_s[step] += std::chrono::duration<double>(t1 - t0).count(); }
         t0 = t1;
     }
 };
@@ -930,6 +931,7 @@ using namespace zk;
 extern "C" {
 
 void zkgpu_prover_step_seconds(double out[8], int reset) {
+    std::lock_guard<std::mutex> lk(g_step_mu);
     for (int i = 0; i < 8; ++i) { out[i] = g_step_s[i]; if (reset) g_step_s[i] = 0; }
 }
 void zkgpu_set_trace(void (*fn)(const char*, const void*, size_t)) { g_trace = fn; }
