@@ -254,3 +254,21 @@ def test_coalesced_single_proof_requests(tiny):
     assert len(co.batches) < 12
     for i, (adv, pi) in wits.items():
         assert got[i] == po.prove(adv, pi, seed=900 + i)
+
+
+@pytest.mark.parametrize("name,k", [("tiny", 5), ("tiny_lookup", 5), ("deposit", 15)])
+def test_extreme_circuit_sizes(name, k):
+    """Smallest domain the shapes allow (k = 5: single-warp NTT tiles, 32-row scans) and a domain larger than
+    Shielder's (k = 15: extended domain 2^18, MSM window c > 13 so the bucket table exceeds shared memory and the
+    global-atomics digit sort runs)."""
+    zkgpu.init(0)
+    shape = circuits.Shape(name, k=k, table_size=8) if "lookup" in name else circuits.Shape(name, k=k)
+    circ = circuits.Circuit(shape, O.OracleBackend, seed=6)
+    srs = O.params_setup(k, 42) if k > 11 else O.downsized_srs(k)
+    po = O.PlonkOracle(circ.blob, srs, threads=8)
+    params = zkgpu.ParamsKZG(k, srs["g"], srs["g_lagrange"])
+    pk = zkgpu.ProvingKey(params, circ.blob)
+    try:
+        _check_batch(shape, circ, po, pk, seeds=[5, 6], witness_seeds=[8, 9], traced=True)
+    finally:
+        pk.release(); params.release()
