@@ -331,6 +331,64 @@ __global__ void __launch_bounds__(ZK_REDUCE_T_LAT) k_msm_reduce(const g1_xyzz_t*
     if (threadIdx.x == 0) xyzz_store(groups + blockIdx.x, part[0]);
 }
 
+// Latency variant of the bucket reduction for a handful of MSMs: ZK_REDUCE_R CTAs of 128 threads share one bucket
+// group (one warp per scheduler, so the dependent additions of a thread run at single-warp latency, on R SMs), the
+// per-thread weights come from a suffix scan instead of a per-thread small scalar multiplication, and a second
+// tiny kernel folds the R partial sums.
+#define ZK_REDUCE_R 8
+__global__ void __launch_bounds__(128) k_msm_reduce_multi(const g1_xyzz_t* __restrict__ buckets, MsmDims D, g1_xyzz_t* __restrict__ partial) {
+    __shared__ g1_xyzz_t sfx[128];   // suffix sums of the segment sums
+    __shared__ g1_xyzz_t wsum[128];  // tree over the weighted segment sums
+    const unsigned T = blockDim.x, t = threadIdx.x;
+    const unsigned grp = blockIdx.x / ZK_REDUCE_R, c = blockIdx.x % ZK_REDUCE_R;
+    const unsigned seg = D.nb / ZK_REDUCE_R;     // buckets of this CTA
+    const unsigned L = seg / T;                  // buckets per thread (host guarantees divisibility, L a power of two)
+    const g1_xyzz_t* B = buckets + (size_t)grp * D.nb + (size_t)c * seg;
+    const unsigned lo = t * L;
+    g1_xyzz_t run = g1_xyzz_t::identity(), acc = g1_xyzz_t::identity();
+    for (unsigned j = L; j-- > 0;) {
+        run = xyzz_add(run, xyzz_load(B + lo + j));
+        acc = xyzz_add(acc, run);
+    }
+    // inclusive suffix scan: sfx[t] = sum_{u >= t} S_u
+    sfx[t] = run;
+    __syncthreads();
+    for (unsigned d = 1; d < T; d <<= 1) {
+        g1_xyzz_t other = g1_xyzz_t::identity();
+        const bool has = t + d < T;
+        if (has) other = sfx[t + d];
+        __syncthreads();
+        if (has) sfx[t] = xyzz_add(sfx[t], other);
+        __syncthreads();
+    }
+    // sum_t (W_t + t L S_t) = sum_t W_t + L * sum_{u >= 1} sfx[u]
+    g1_xyzz_t v = acc;
+    if (t >= 1) {
+        g1_xyzz_t x = sfx[t];
+        for (unsigned l = 1; l < L; l <<= 1) x = xyzz_dbl(x);
+        v = xyzz_add(v, x);
+    }
+    wsum[t] = v;
+    __syncthreads();
+    for (unsigned s2 = T >> 1; s2 > 0; s2 >>= 1) {
+        if (t < s2) wsum[t] = xyzz_add(wsum[t], wsum[t + s2]);
+        __syncthreads();
+    }
+    if (t == 0) {
+        // bucket b of this CTA has global weight c*seg + b + 1: add (c * seg) * (sum of the CTA's buckets)
+        g1_xyzz_t r = wsum[0];
+        if (c) r = xyzz_add(r, xyzz_mul_small(sfx[0], c * seg));
+        xyzz_store(partial + blockIdx.x, r);
+    }
+}
+__global__ void k_msm_reduce_fold(const g1_xyzz_t* __restrict__ partial, g1_xyzz_t* __restrict__ groups, unsigned count) {
+    unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= count) return;
+    g1_xyzz_t acc = xyzz_load(partial + (size_t)g * ZK_REDUCE_R);
+    for (unsigned c = 1; c < ZK_REDUCE_R; ++c) acc = xyzz_add(acc, xyzz_load(partial + (size_t)g * ZK_REDUCE_R + c));
+    xyzz_store(groups + g, acc);
+}
+
 __global__ void k_msm_combine(const g1_xyzz_t* __restrict__ groups, MsmDims D, size_t M, g1_xyzz_t* __restrict__ out) {
     size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
@@ -422,7 +480,7 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
     const size_t total = M * plan.n;
     ZK_REQUIRE(K <= (1u << 30), "msm: too many buckets");
     const size_t sort_smem = (K + 1024 + D.heavy + 2) * sizeof(uint32_t);
-    if (K <= 8192 && plan.n <= (1u << 20)) {
+    if (K <= 8192 && plan.n <= (1u << 20) && M >= 32) {   // one CTA per MSM: needs enough MSMs to fill the GPU
         KtScope kt(KT_MSM_SORT, st);
         static std::once_flag sort_once;
         std::call_once(sort_once, [] { ZK_CUDA(cudaFuncSetAttribute(k_msm_sort_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); });
@@ -448,6 +506,15 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
         ZK_LAUNCH(k_msm_heavy, 148 * 8, 128, 0, st, d_bases, ws.offsets.p, ws.entries.p, D, ws.buckets.p, ws.heavy_count.p, ws.heavy_list.p);
     }
     KtScope kt(KT_MSM_REDUCE, st);
+    if (M * plan.G <= 64 && plan.nb >= ZK_REDUCE_R * 128) {
+        // latency regime: R CTAs per bucket group, then fold
+        g1_xyzz_t* groups = plan.precomp ? d_out : ws.groups.p;
+        ws.partial.ensure(M * plan.G * ZK_REDUCE_R);
+        ZK_LAUNCH(k_msm_reduce_multi, (unsigned)(M * plan.G * ZK_REDUCE_R), 128, 0, st, ws.buckets.p, D, ws.partial.p);
+        ZK_LAUNCH(k_msm_reduce_fold, ceil_div(M * plan.G, 32), 32, 0, st, ws.partial.p, groups, (unsigned)(M * plan.G));
+        if (!plan.precomp) ZK_LAUNCH(k_msm_combine, ceil_div(M, 64), 64, 0, st, ws.groups.p, D, M, d_out);
+        return;
+    }
     unsigned Tmax = M * plan.G < 148 * 4 ? ZK_REDUCE_T_LAT : ZK_REDUCE_T;
     unsigned T = plan.nb < Tmax ? plan.nb : Tmax;
     g1_xyzz_t* groups = plan.precomp ? d_out : ws.groups.p;

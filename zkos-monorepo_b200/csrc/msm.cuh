@@ -27,6 +27,7 @@ struct MsmWorkspace {
     DevBuf<uint32_t> entries;   // M * n * W
     DevBuf<g1_xyzz_t> buckets;  // M * K
     DevBuf<g1_xyzz_t> groups;   // M * G
+    DevBuf<g1_xyzz_t> partial;  // latency regime: R partial sums per bucket group
     DevBuf<uint32_t> order;     // M * K bucket keys by decreasing run length
     DevBuf<uint32_t> heavy_count;  // worklist of buckets with long runs (k_msm_heavy)
     DevBuf<uint64_t> heavy_list;
