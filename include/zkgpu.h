@@ -86,6 +86,10 @@ int zkgpu_params_setup(uint32_t k, uint64_t seed, uint64_t* g_out, uint64_t* g_l
 
 /* g_lagrange_out may be NULL (then k up to 24: bases for the large-MSM sweep). */
 
+/* Counts the points that are neither the identity (0,0) nor on y^2 = x^3 + 3: the `G1Affine::from_xy(..).unwrap()`
+ * check of the ptau reader (/root/reference/crates/powers-of-tau/lib.rs:206-224). */
+int zkgpu_g1_on_curve(const uint64_t* points_affine, size_t n, uint64_t* bad_count);
+
 /* Host-side sum of n affine points: the combine step of a point-sharded MSM (one partial result per GPU,
  * gathered by the caller).  Needs no GPU. */
 int zkgpu_g1_sum_affine(const uint64_t* points_affine, size_t n, uint64_t out_affine[8]);

@@ -28,6 +28,7 @@ extern "C" {
     pub fn zkgpu_g_to_lagrange(g_affine: *const u64, k: u32, out_affine: *mut u64) -> c_int;
     pub fn zkgpu_params_setup(k: u32, seed: u64, g_out: *mut u64, g_lagrange_out: *mut u64) -> c_int;
     pub fn zkgpu_g1_sum_affine(points_affine: *const u64, n: usize, out_affine: *mut u64) -> c_int;
+    pub fn zkgpu_g1_on_curve(points_affine: *const u64, n: usize, bad_count: *mut u64) -> c_int;
 
     pub fn zkgpu_pk_create(srs: u64, circuit_blob: *const u8, blob_len: usize, pk_out: *mut u64) -> c_int;
     pub fn zkgpu_pk_release(pk: u64) -> c_int;

@@ -18,9 +18,43 @@ __global__ void __launch_bounds__(64) k_fixed_base_mul(const fr_t* __restrict__ 
     fe_store(&out[i].x, r.x); fe_store(&out[i].y, r.y); fe_store(&out[i].zz, r.zz); fe_store(&out[i].zzz, r.zzz);
 }
 
+// y^2 == x^3 + 3 (or the identity (0,0)) for every point: `G1Affine::from_xy(x, y).unwrap()` of the ptau reader
+// (/root/reference/crates/powers-of-tau/lib.rs:206-224)
+__global__ void k_g1_on_curve(const g1_affine_t* __restrict__ pts, size_t n, unsigned long long* __restrict__ bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_affine_t p;
+    p.x = fe_load(&pts[i].x); p.y = fe_load(&pts[i].y);
+    if (p.is_identity()) return;
+    fq_t three = fq_t::zero(); three.l[0] = 3; three = to_mont(three);
+    if (!(sqr(p.y) == sqr(p.x) * p.x + three)) atomicAdd(bad, 1ull);
+}
+
 }  // namespace zk
 
 using namespace zk;
+
+extern "C" int zkgpu_g1_on_curve(const uint64_t* points_affine, size_t n, uint64_t* bad_count) {
+    try {
+        std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+        Context& C = ctx(); C.require();
+        ZK_REQUIRE((points_affine || n == 0) && bad_count, "null pointer");
+        *bad_count = 0;
+        if (!n) return ZKGPU_OK;
+        cudaStream_t st = C.stream;
+        C.pt_buf.ensure(n);
+        DevBuf<unsigned long long> d_bad(1);
+        ZK_CUDA(cudaMemsetAsync(d_bad.p, 0, 8, st));
+        ZK_CUDA(cudaMemcpyAsync(C.pt_buf.p, points_affine, n * 64, cudaMemcpyHostToDevice, st));
+        ZK_LAUNCH(k_g1_on_curve, ceil_div(n, 128), 128, 0, st, C.pt_buf.p, n, d_bad.p);
+        unsigned long long bad = 0;
+        ZK_CUDA(cudaMemcpyAsync(&bad, d_bad.p, 8, cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(cudaStreamSynchronize(st));
+        *bad_count = bad;
+        return ZKGPU_OK;
+    } catch (const zk::Error& e) { g_last_error = e.what(); return e.code; }
+    catch (const std::exception& e) { g_last_error = e.what(); return ZKGPU_ERR_INTERNAL; }
+}
 
 extern "C" int zkgpu_params_setup(uint32_t k, uint64_t seed, uint64_t* g_out, uint64_t* g_lagrange_out) {
     try {
