@@ -1,0 +1,161 @@
+"""Byte-layout contract at the prover boundary — host mirror of `crates/type-conversions`
+(/root/reference/crates/type-conversions/lib.rs:34-118, endianess.rs:3-34) and of the witness decoders of the
+bindings (`vec_to_f`, `vec_to_path`: /root/reference/crates/shielder_bindings/src/utils.rs:32-60).
+
+A field element on the Python side is what crosses the C ABI: four little-endian u64 limbs in Montgomery form
+(numpy uint64[4], the memory of Rust `bn256::Fr`).  U256 values are Python ints, addresses 20-byte `bytes`.
+These are scalar host-side codecs (a handful per proof), not part of the GPU path.
+"""
+import numpy as np
+
+R_MOD = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+_MONT_R = 1 << 256
+_MONT_R_INV = pow(_MONT_R, -1, R_MOD)
+ARITY, NOTE_TREE_HEIGHT = 7, 13          # crates/shielder-setup/lib.rs:4-5
+FR_SIZE = 32
+
+
+class ConversionError(ValueError):
+    pass
+
+
+class IncorrectVecLength(ConversionError):
+    def __init__(self, expected, actual):
+        super().__init__("incorrect vec length: expected %d, got %d" % (expected, actual))
+        self.expected, self.actual = expected, actual
+
+
+class Halo2FieldElementCreationFailed(ConversionError):
+    def __init__(self):
+        super().__init__("halo2 failed to create field element")
+
+
+class HexU256ParseError(ConversionError):
+    def __init__(self):
+        super().__init__("failed to parse hex string to U256")
+
+
+def _to_limbs(v):
+    return np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
+def _from_limbs(f):
+    f = np.asarray(f, dtype=np.uint64).reshape(4)
+    return sum(int(f[i]) << (64 * i) for i in range(4))
+
+
+def fr(value):
+    """`Fr::from(u64)` / from any integer: Montgomery limbs of value mod r"""
+    return _to_limbs((int(value) % R_MOD) * _MONT_R % R_MOD)
+
+
+def fr_value(f):
+    """canonical integer of a field element"""
+    return _from_limbs(f) * _MONT_R_INV % R_MOD
+
+
+def u256_to_field(value):
+    """lib.rs:35-37 — `F::from(limbs)`: the 256-bit integer reduced into the field"""
+    if not 0 <= int(value) < 1 << 256:
+        raise ConversionError("not a U256")
+    return fr(value)
+
+
+def field_to_u256(f):
+    """lib.rs:40-44 — `U256::from_le_bytes(to_repr())`"""
+    return fr_value(f)
+
+
+def _array(data, length):
+    data = bytes(data)
+    if len(data) != length:
+        raise IncorrectVecLength(length, len(data))
+    return data
+
+
+def bytes_to_field(data):
+    """lib.rs:59-66 — `F::from_repr`: 32 little-endian bytes of a CANONICAL value (< r), else an error"""
+    v = int.from_bytes(_array(data, FR_SIZE), "little")
+    if v >= R_MOD:
+        raise Halo2FieldElementCreationFailed()
+    return fr(v)
+
+
+def field_to_bytes(f):
+    """lib.rs:69-73 — `to_repr()`: canonical little-endian"""
+    return fr_value(f).to_bytes(FR_SIZE, "little")
+
+
+def hex_to_u256(text):
+    """lib.rs:82-84 — hex string with 0x prefix"""
+    try:
+        if not text.startswith("0x"):
+            raise ValueError
+        v = int(text[2:], 16)
+    except ValueError:
+        raise HexU256ParseError()
+    if v >= 1 << 256:
+        raise HexU256ParseError()
+    return v
+
+
+def hex_32_to_f(text):
+    return u256_to_field(hex_to_u256(text))
+
+
+def bytes_to_u256(data):
+    return int.from_bytes(_array(data, 32), "little")
+
+
+def u256_to_bytes(value):
+    return int(value).to_bytes(32, "little")
+
+
+def address_to_u256(address):
+    return int.from_bytes(_array(address, 20), "big")
+
+
+def address_to_field(address):
+    """lib.rs:97-102 — `uint256(uint160(address))`"""
+    return u256_to_field(address_to_u256(address))
+
+
+def field_to_address(f):
+    """lib.rs:105-113 — low 20 bytes of the big-endian representation"""
+    return to_bytes_be(f)[12:]
+
+
+# ---- Endianess trait (endianess.rs) ----------------------------------------------------------------------
+def to_bytes_le(f):
+    return field_to_bytes(f)
+
+
+def to_bytes_be(f):
+    return field_to_bytes(f)[::-1]
+
+
+def from_bytes_le(data):
+    return bytes_to_field(data)
+
+
+def from_bytes_be(data):
+    return bytes_to_field(_array(data, FR_SIZE)[::-1])
+
+
+# ---- witness decoders of the bindings --------------------------------------------------------------------
+def vec_to_f(v):
+    """utils.rs:32-34"""
+    return bytes_to_field(v)
+
+
+def vec_to_path(v):
+    """utils.rs:36-60 — NOTE_TREE_HEIGHT x ARITY field elements from 7 * 13 * 32 = 2912 bytes"""
+    v = bytes(v)
+    if len(v) != NOTE_TREE_HEIGHT * ARITY * FR_SIZE:
+        raise IncorrectVecLength(NOTE_TREE_HEIGHT * ARITY * FR_SIZE, len(v))
+    out = np.empty((NOTE_TREE_HEIGHT, ARITY, 4), dtype=np.uint64)
+    for i in range(NOTE_TREE_HEIGHT):
+        for j in range(ARITY):
+            o = (i * ARITY + j) * FR_SIZE
+            out[i, j] = bytes_to_field(v[o:o + FR_SIZE])
+    return out
