@@ -62,7 +62,8 @@ __device__ __forceinline__ void tile_st(uint4* sm, unsigned total, unsigned e, c
 
 // One tile pass.  Radix-2 DIT stages run three at a time on 8 register-resident elements per thread (12
 // butterflies between two __syncthreads), so a 256-point column costs 3 shared-memory round trips, not 8.
-__global__ void __launch_bounds__(512) k_ntt_tile(const NttPass P) {
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_ntt_tile(const NttPass P) {
     extern __shared__ uint4 sm4[];
     const unsigned log_m = P.log_m, log_C = P.log_C;
     const unsigned m = 1u << log_m, C = 1u << log_C, log_total = log_m + log_C, total = 1u << log_total;
@@ -259,15 +260,17 @@ static void launch_pass(const NttPass& P, size_t batch, cudaStream_t st) {
     {
         std::lock_guard<std::mutex> lk(mu);
         int dev; ZK_CUDA(cudaGetDevice(&dev));
-        if (smem > 48 * 1024 && cur[dev] < smem) {
-            ZK_CUDA(cudaFuncSetAttribute(k_ntt_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (cur[dev] < 200 * 1024) {
+            ZK_CUDA(cudaFuncSetAttribute(k_ntt_tile<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            ZK_CUDA(cudaFuncSetAttribute(k_ntt_tile<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
             cur[dev] = 200 * 1024;
         }
     }
     size_t blocks = batch * P.tiles_per_poly;
     ZK_REQUIRE(blocks < (1ull << 31), "ntt: grid too large");
     KtScope kt(KT_NTT, st);
-    ZK_LAUNCH(k_ntt_tile, (unsigned)blocks, threads, smem, st, P);
+    if (threads <= 256 && smem <= 72 * 1024) ZK_LAUNCH((k_ntt_tile<256, 2>), (unsigned)blocks, threads, smem, st, P);
+    else ZK_LAUNCH((k_ntt_tile<512, 1>), (unsigned)blocks, threads, smem, st, P);
 }
 
 static unsigned pick_swz(unsigned log_m, unsigned log_C) {
