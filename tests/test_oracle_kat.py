@@ -14,7 +14,7 @@ import pytest
 import oracle_lib as O
 import pyref as P
 
-REF_PTAU = "/root/reference/resources/ppot_0080_11.ptau"
+REF_PTAU = os.path.join(O.GOLDEN, "ppot_0080_11.ptau")   # copy of the reference's resources/ppot_0080_11.ptau
 rng = np.random.default_rng(1234)
 
 
@@ -111,7 +111,6 @@ def test_srs_raw_parse(raw11):
     assert g2[0] == 0x1800DEEF121F1E76426A00665E5C4479674322D4F75EDADD46DEBD5CD992F6ED  # BN254 G2 generator x.c0
 
 
-@pytest.mark.skipif(not os.path.exists(REF_PTAU), reason="reference tree not present (GPU box)")
 def test_raw_equals_perpetual(raw11):
     """crates/powers-of-tau/lib.rs:267-281"""
     pt = O.srs_read(REF_PTAU, 1)
