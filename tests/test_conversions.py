@@ -72,3 +72,22 @@ def test_vec_to_path():
     assert np.array_equal(cv.vec_to_f(raw[:32]), path[0, 0])
     with pytest.raises(cv.IncorrectVecLength):
         cv.vec_to_path(raw[:-32])
+
+
+def test_encode_calldata():
+    """ABI layout the generated verifier checks (templates/Halo2Verifier.sol:75-83, 240-263): selector, offsets 0x40 and
+    0x40 + 0x20 + len(proof), proof length, instance count, instance words."""
+    assert cv.VERIFY_PROOF_SELECTOR == O.keccak256(b"verifyProof(bytes,uint256[])")[:4]
+    proof = bytes(range(256)) * 19 + bytes(224)          # 5088 bytes: the withdraw shape's proof length (a word multiple)
+    inst = [cv.fr(v) for v in (1, 2, cv.R_MOD - 1)]
+    cd = cv.encode_calldata(proof, inst)
+    assert cd[:4] == cv.VERIFY_PROOF_SELECTOR
+    w = lambda i: int.from_bytes(cd[4 + 32 * i: 36 + 32 * i], "big")
+    assert w(0) == 0x40 and w(1) == 0x40 + 0x20 + len(proof) and w(2) == len(proof)
+    assert cd[4 + 96: 4 + 96 + len(proof)] == proof
+    base = 3 + len(proof) // 32
+    assert [w(base), w(base + 1), w(base + 2), w(base + 3)] == [3, 1, 2, cv.R_MOD - 1]
+    assert len(cd) == 4 + 32 * (base + 4)
+    # unaligned proofs are zero-padded to a word boundary
+    cd2 = cv.encode_calldata(b"\x01\x02\x03", [])
+    assert len(cd2) == 4 + 32 * 5 and cd2[4 + 96: 4 + 128] == b"\x01\x02\x03" + bytes(29)

@@ -159,3 +159,20 @@ def vec_to_path(v):
             o = (i * ARITY + j) * FR_SIZE
             out[i, j] = bytes_to_field(v[o:o + FR_SIZE])
     return out
+
+
+# ---- calldata of the on-chain verifier -------------------------------------------------------------------
+VERIFY_PROOF_SELECTOR = bytes.fromhex("1e8e1e13")   # keccak256("verifyProof(bytes,uint256[])")[:4]
+
+
+def encode_calldata(proof, instances):
+    """`verifier_contract::encode_calldata(proof, instances)`
+    (/root/reference/crates/halo2-verifier/src/lib/verifier_contract.rs:14-20): Solidity ABI encoding of
+    `Halo2Verifier.verifyProof(bytes proof, uint256[] instances)` — selector, two head offsets, the proof as
+    length-prefixed bytes padded to a word, the instances as length-prefixed big-endian words."""
+    proof = bytes(proof)
+    word = lambda v: int(v).to_bytes(32, "big")
+    padded = proof + b"\x00" * (-len(proof) % 32)
+    inst = [field_to_u256(f) for f in instances]
+    head = word(0x40) + word(0x40 + 32 + len(padded))
+    return VERIFY_PROOF_SELECTOR + head + word(len(proof)) + padded + word(len(inst)) + b"".join(word(v) for v in inst)
