@@ -26,6 +26,9 @@
 #include <map>
 #include <set>
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace oracle {
 
@@ -443,6 +446,14 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
     const size_t unusable_start = n - (bf + 1);
     ProverStats st;
     if (stats) st.trace = stats->trace;
+    const bool timing = getenv("ORACLE_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[oracle] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     auto trace = [&](const char* name, const std::vector<Fr>& v) { if (st.trace) st.trace(name, v.data(), v.size()); };
     auto trace2 = [&](const char* name, const std::vector<std::vector<Fr>>& vv) { if (st.trace) for (auto& v : vv) st.trace(name, v.data(), v.size()); };
     if (advice.size() != cs.num_advice) throw std::runtime_error("create_proof: wrong number of advice columns");
@@ -462,6 +473,7 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
     trace2("advice_blinded", advice);
     for (auto& col : advice) { tr.write_point(params.commit_lagrange(col)); st.msms++; }
 
+    lap("advice blind+commit");
     Fr theta = tr.squeeze_challenge();
 
     // lookup arguments, part 1 (halo2 lookup/prover.rs commit_permuted): compress the input / table expressions with
@@ -517,6 +529,7 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
         trace2("lookup_permuted_table", lk_s);
     }
 
+    lap("lookup permuted");
     Fr beta = tr.squeeze_challenge(), gamma = tr.squeeze_challenge();
 
     // permutation grand products
@@ -555,6 +568,7 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
         }
     }
 
+    lap("permutation z + commit + ntt");
     // lookup arguments, part 2 (commit_product): z[0] = 1, z[i+1] = z[i] (A_i + beta)(S_i + gamma) / ((A'_i + beta)(S'_i + gamma))
     std::vector<std::vector<Fr>> lk_z_polys(L), lk_a_polys(L), lk_s_polys(L), lk_z_cosets(L), lk_a_cosets(L), lk_s_cosets(L);
     for (size_t l = 0; l < L; ++l) {
@@ -577,6 +591,7 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
         lk_s_cosets[l] = d.coeff_to_extended(lk_s_polys[l]); st.ext_ntts++;
     }
 
+    lap("lookup z");
     // vanishing argument: random polynomial (single-thread ChaCha20 stream)
     std::vector<Fr> random_poly(n);
     {
@@ -588,6 +603,7 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
         tr.write_point(params.commit(random_poly)); st.msms++;
     }
 
+    lap("random poly + commit");
     Fr y = tr.squeeze_challenge();
 
     std::vector<std::vector<Fr>> advice_polys;
@@ -596,6 +612,7 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
     trace2("advice_poly", advice_polys);
     trace2("z_poly", z_polys);
     trace2("z_coset", z_cosets);
+    lap("advice intt");
     // evaluate_h on the extended coset
     std::vector<Fr> h(en, Fr::zero());
     {
@@ -665,6 +682,7 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
         });
     }
 
+    lap("coset ntt + evaluate_h");
     // vanishing construct: divide by X^n - 1 on the coset, back to coefficients, split, commit pieces
     d.divide_by_vanishing_poly(h);
     trace("h_evals", h);
@@ -676,6 +694,7 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
     for (unsigned i = 0; i < Q; ++i) (void)random_field<Fr>(rng);  // h_blinds
     for (auto& p : h_pieces) { tr.write_point(params.commit(p)); st.msms++; }
 
+    lap("h: intt + commit pieces");
     Fr x = tr.squeeze_challenge();
     Fr xn = x.pow_u64(n);
 
@@ -704,6 +723,7 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
     for (auto& e : evals) tr.write_scalar(e);
     evals.push_back(eval_polynomial(h_poly.data(), n, x));  // "computed" quotient eval: not written
 
+    lap("evaluations");
     // SHPLONK multiopen
     QueryPlan plan(cs);
     auto poly_of = [&](int id) -> const std::vector<Fr>& {
@@ -746,6 +766,7 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
     }
     trace2("set_combined", set_combined);
     trace("hx", hx);
+    lap("shplonk h(X) build");
     tr.write_point(params.commit(hx)); st.msms++;
     Fr mu = tr.squeeze_challenge();
     {
@@ -769,6 +790,7 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
         trace("wq", wq);
         tr.write_point(params.commit(wq)); st.msms++;
     }
+    lap("shplonk rest");
     if (stats) { stats->msms = st.msms; stats->ntts = st.ntts; stats->ext_ntts = st.ext_ntts; }
     if (tr.proof.size() != cs.proof_len()) throw std::runtime_error("create_proof: proof length mismatch");
     return tr.proof;
