@@ -1002,4 +1002,39 @@ static inline bool verify_proof(const ParamsKZG& params, const VerifyingKey& vk,
     return ok;
 }
 
+// Batch verification with a random linear combination of the pairing inputs: every proof is replayed to
+// its (lhs_i, rhs_i); accept iff e(sum r_i lhs_i, g2) * e(-sum r_i rhs_i, s_g2) == 1 for random r_i.  Sound up to 1/r.
+// Returns the number of proofs that failed BEFORE the pairing (malformed, wrong length); `all_ok` is the batched check.
+static inline size_t verify_proofs_batch(const ParamsKZG& params, const VerifyingKey& vk, const uint8_t* proofs, size_t proof_len, size_t m,
+                                         const Fr* instances, size_t n_inst, unsigned threads, u64 seed, bool& all_ok) {
+    std::vector<PairingInputs> pi(m);
+    std::vector<uint8_t> good(m, 0);
+    parallel_chunks(m, threads, [&](size_t a, size_t b) {
+        for (size_t i = a; i < b; ++i) {
+            std::vector<Fr> inst(instances + i * n_inst, instances + (i + 1) * n_inst);
+            good[i] = verify_proof_to_pairing(params, vk, proofs + i * proof_len, proof_len, inst, pi[i]) ? 1 : 0;
+        }
+    });
+    size_t bad = 0;
+    for (auto g : good) bad += g ? 0 : 1;
+    SmallRng rng(seed);
+    std::vector<G1> lp(threads ? threads : 1, G1::identity()), rp(lp);
+    std::vector<Fr> r(m);
+    for (auto& x : r) x = random_field<Fr>(rng);
+    size_t nchunks = lp.size(), chunk = (m + nchunks - 1) / nchunks;
+    parallel_chunks(nchunks, threads, [&](size_t a, size_t b) {
+        for (size_t c = a; c < b; ++c)
+            for (size_t i = c * chunk; i < std::min(m, (c + 1) * chunk); ++i) {
+                if (!good[i]) continue;
+                lp[c] = lp[c].add(G1::from_affine(pi[i].lhs).mul(r[i]));
+                rp[c] = rp[c].add(G1::from_affine(pi[i].rhs).mul(r[i]));
+            }
+    });
+    G1 L = G1::identity(), R = G1::identity();
+    for (auto& x : lp) L = L.add(x);
+    for (auto& x : rp) R = R.add(x);
+    all_ok = bad == 0 && pairing_product_is_one(L.to_affine(), params.g2, R.to_affine().neg(), params.s_g2);
+    return bad;
+}
+
 }  // namespace oracle

@@ -276,6 +276,16 @@ class PlonkOracle:
         _chk(lib().orc_plonk_verify(self.h, proof, C.c_size_t(len(proof)), _p(instance), C.c_size_t(instance.size // 4), C.byref(ok)))
         return bool(ok.value)
 
+    def verify_batch(self, proofs, instances, threads=8):
+        """all proofs of a batch at once (RLC of the pairing inputs): returns (all accepted, number malformed)"""
+        blob = b"".join(proofs) if not isinstance(proofs, (bytes, bytearray)) else bytes(proofs)
+        instances = np.ascontiguousarray(instances, dtype=np.uint64)
+        m = len(blob) // self.proof_len
+        ok, bad = C.c_int(0), C.c_uint64(0)
+        _chk(lib().orc_plonk_verify_batch(self.h, blob, C.c_size_t(self.proof_len), C.c_size_t(m), _p(instances),
+                                          C.c_size_t(instances.size // (4 * m)), threads, C.byref(ok), C.byref(bad)))
+        return bool(ok.value), int(bad.value)
+
     def __del__(self):
         try:
             lib().orc_plonk_free(self.h)

@@ -110,3 +110,18 @@ def test_lookup_circuits_prove_verify(name):
     assert not ok and "lookup" in msg
     with pytest.raises(RuntimeError):
         po.prove(bad, pi, seed=1)
+
+
+def test_batch_verification(setup):
+    """Random-linear-combination batch verifier: accepts a batch of valid proofs, rejects if any one is altered."""
+    shape, circ, po = setup
+    wits = [circ.witness(40 + i) for i in range(6)]
+    proofs = [po.prove(a, p, seed=i) for i, (a, p) in enumerate(wits)]
+    inst = np.stack([p for _, p in wits])
+    assert po.verify_batch(proofs, inst, threads=4) == (True, 0)
+    bad = list(proofs)
+    b = bytearray(bad[3]); b[len(b) - 40] ^= 1; bad[3] = bytes(b)           # an evaluation word: pairing must fail
+    ok, malformed = po.verify_batch(bad, inst, threads=4)
+    assert not ok
+    wrong = inst.copy(); wrong[2, 0] = O.OracleBackend.const(7)
+    assert po.verify_batch(proofs, wrong, threads=4)[0] is False
