@@ -272,3 +272,23 @@ def test_extreme_circuit_sizes(name, k):
         _check_batch(shape, circ, po, pk, seeds=[5, 6], witness_seeds=[8, 9], traced=True)
     finally:
         pk.release(); params.release()
+
+
+def test_two_pipeline_workers_and_ragged_sub_batches(tiny, monkeypatch):
+    """m = 11 proofs with ZKGPU_PROVER_BATCH=3: four sub-batches (3, 3, 3, 2) alternate between the two pipeline workers
+    (host thread + stream + workspace each); every proof must still be the oracle's, in request order, and the batch
+    verifier must accept the whole set."""
+    shape, circ, po, params, pk = tiny
+    monkeypatch.setenv("ZKGPU_PROVER_BATCH", "3")
+    wits = [circ.witness(60 + i) for i in range(11)]
+    adv = np.stack([w[0] for w in wits]); inst = np.stack([w[1] for w in wits])
+    seeds = np.arange(11, dtype=np.uint64) + 500
+    proofs = pk.prove_batch(adv, inst, seeds)
+    for i in range(11):
+        assert proofs[i] == po.prove(adv[i], inst[i], seed=int(seeds[i])), i
+    assert po.verify_batch(proofs, inst, threads=4) == (True, 0)
+    # the device-resident entry point gives the same bytes
+    import torch
+    d_adv = torch.from_numpy(adv.view(np.int64)).cuda()
+    out = pk.prove_batch_dev(d_adv.data_ptr(), inst, seeds)
+    assert out.tobytes() == b"".join(proofs)
