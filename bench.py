@@ -264,8 +264,10 @@ def main():
     W_win, c_win = 254 // 13 + 1, 13
     msm_per_proof = shape.num_msm
     fmul_bucket = ksteps * M * msm_per_proof * n * W_win * 10
-    en = 1 << shape.extended_k
-    ntt_bytes_proof = shape.num_ntt * 64 * n + (shape.num_ext_ntt - 1) * (32 * n + 32 * en) + 64 * en
+    # the quotient is evaluated on num_quotients cosets of the size-n subgroup (not on halo2's whole 2^extended_k domain):
+    # every extended column = one read of n coefficients + Qc size-n transforms written; h = Qc in-place size-n inverse transforms
+    cn = shape.num_quotients * n
+    ntt_bytes_proof = shape.num_ntt * 64 * n + (shape.num_ext_ntt - 1) * (32 * n + 32 * cn) + 64 * cn
     ntt_bytes = ksteps * M * ntt_bytes_proof
     total_k_ms = sum(v[0] for v in ktimes.values()) or 1.0
     dom = max(ktimes, key=lambda k_: ktimes[k_][0])
@@ -320,7 +322,7 @@ def main():
             "dtype": "u32x8 (254-bit Montgomery)", "data": "synthetic",
             "config": {"workload": "batch of %d withdraw-shaped proofs per GPU (BASELINE configs[3])" % M, "shape": args.shape, "k": shape.k,
                        "extended_k": shape.extended_k, "advice_columns": A, "msm_per_proof": shape.num_msm, "ntt_per_proof": shape.num_ntt,
-                       "ext_ntt_per_proof": shape.num_ext_ntt, "proof_bytes": pk.proof_len, "sub_batch": pk.sub_batch, "msm_window_bits": c_win,
+                       "ext_ntt_per_proof": shape.num_ext_ntt, "quotient_cosets": shape.num_quotients, "proof_bytes": pk.proof_len, "sub_batch": pk.sub_batch, "msm_window_bits": c_win,
                        "srs": "ParamsKZG::setup seed 42 (ppot_0080_13 absent from the reference tree)",
                        "l2": "inputs larger than L2 (%.1f GB of advice per step)" % (M * A * n * 32 / 1e9), "parallelism": "dp%d, no collective" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

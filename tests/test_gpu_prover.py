@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
+import pyref as P
 import zkgpu
 from zkgpu import circuits
 
@@ -125,8 +126,14 @@ def test_unsatisfied_witness_rejected(tiny):
     adv, pi = circ.witness(5)
     adv[shape.c[0], 7] = O.OracleBackend.const(99)
     proof = pk.prove(adv, pi, 1)
-    assert proof == po.prove(adv, pi, seed=1)
+    # An unsatisfied witness makes the quotient numerator indivisible by X^n - 1: there is no quotient polynomial, and what a
+    # prover writes from the quotient commitments on depends on how many cosets it evaluates (halo2: all 2^(ek-k), truncated;
+    # this library: num_quotients).  Everything before the quotient commitments is still byte-identical; the proof must not verify.
+    want = po.prove(adv, pi, seed=1)
+    prefix = 64 * (shape.num_advice + 3 * len(shape.lookups) + shape.num_perm_sets + 1)
+    assert len(proof) == len(want) and proof[:prefix] == want[:prefix]
     assert not po.verify(proof, pi)
+    assert not po.verify(want, pi)
 
 
 def test_wrong_sizes_raise(tiny):
@@ -292,3 +299,40 @@ def test_two_pipeline_workers_and_ragged_sub_batches(tiny, monkeypatch):
     d_adv = torch.from_numpy(adv.view(np.int64)).cuda()
     out = pk.prove_batch_dev(d_adv.data_ptr(), inst, seeds)
     assert out.tobytes() == b"".join(proofs)
+
+
+def test_concurrent_api_callers_and_reinit(tiny):
+    """The reference's hosts call the prover from arbitrary threads (tokio tasks, rayon workers): concurrent calls into
+    the C ABI serialise on the library's context and stay correct; shutdown + init gives a working library again."""
+    import threading
+    shape, circ, po, params, pk = tiny
+    wits = {i: circ.witness(80 + i) for i in range(6)}
+    got, errs = {}, []
+
+    def client(i):
+        try:
+            got[i] = pk.prove(wits[i][0], wits[i][1], 700 + i)
+            a = O.random_fr(i, 64)
+            w = O.to_mont(0, P.int_to_limbs([P.omega_for(6)]))[0]
+            assert np.array_equal(zkgpu.best_fft(a, w, 6).reshape(-1, 4), O.fft(a, w, 6).reshape(-1, 4))
+        except Exception as e:  # noqa
+            errs.append(e)
+    ts = [threading.Thread(target=client, args=(i,)) for i in wits]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for i, (adv, pi) in wits.items():
+        assert got[i] == po.prove(adv, pi, seed=700 + i)
+    # shutdown releases every handle; a fresh init + registration works
+    zkgpu.shutdown()
+    with pytest.raises(zkgpu.ZkGpuError):
+        pk.prove(wits[0][0], wits[0][1], 1)           # stale handle
+    zkgpu.init(0)
+    srs = O.downsized_srs(shape.k)
+    p2 = zkgpu.ParamsKZG(shape.k, srs["g"], srs["g_lagrange"])
+    k2 = zkgpu.ProvingKey(p2, circ.blob)
+    assert k2.prove(wits[0][0], wits[0][1], 700) == got[0]
+    k2.release(); p2.release()
+    pk.handle = 0; params.handle = 0                   # the module fixture's handles died with the shutdown

@@ -40,6 +40,8 @@ struct NttPass {
     int has_scale;
     int first_window_trivial;  // inputs are zero for sequence index j >= m/8: the first three stages only replicate
     fr_t scale, cs1, cs2;
+    const fr_t* pre_table;     // optional: input element gi of polynomial p is multiplied by pre_table[(p % pre_count) << log_N | gi]
+    unsigned pre_count;
 };
 
 // Shared-memory tile: two planes of uint4 (low / high 16 bytes of every element), element e of the tile at
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_ntt_tile(const NttPass P) {
             unsigned r3 = (unsigned)(gi % 3);
             if (r3 == 1) v = v * P.cs1; else if (r3 == 2) v = v * P.cs2;
         }
+        if (P.pre_table && valid) v = v * fe_ldg(P.pre_table + (((size_t)(poly % P.pre_count)) << P.log_N) + gi);
         unsigned p = __brev(j) >> (32 - log_m);
         tile_st(sm4, total, (p << log_C) | c, v);
     }
@@ -246,6 +249,16 @@ const fr_t* ntt_twiddles(unsigned log_n, const fr_t& omega, cudaStream_t st) {
     g_tw.emplace(key, std::move(d_tw));
     return p;
 }
+void fr_power_table(fr_t* d_out, unsigned log_count, const fr_t& base, cudaStream_t st) {
+    std::vector<fr_t> pows(log_count ? log_count : 1);
+    fr_t w = base;
+    for (unsigned b = 0; b < pows.size(); ++b) { pows[b] = w; w = sqr(w); }
+    DevBuf<fr_t> d_pows(pows.size());
+    ZK_CUDA(cudaMemcpyAsync(d_pows.p, pows.data(), pows.size() * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+    size_t count = (size_t)1 << log_count;
+    ZK_LAUNCH(k_twiddles, ceil_div(count, 256), 256, 0, st, d_out, count, d_pows.p, log_count);
+    ZK_CUDA(cudaStreamSynchronize(st));
+}
 void ntt_clear_cache() {
     std::lock_guard<std::mutex> lk(g_tw_mu);
     g_tw.clear();
@@ -295,7 +308,8 @@ void ntt_run(const NttJob& J, cudaStream_t st) {
     NttPass P;
     memset(&P, 0, sizeof P);
     P.tw = tw; P.log_N = log_N;
-    P.in_poly_stride = J.in_stride ? J.in_stride : N;
+    P.in_poly_stride = J.in_broadcast ? 0 : (J.in_stride ? J.in_stride : N);
+    P.pre_table = J.pre_table; P.pre_count = J.pre_count ? J.pre_count : 1;
     P.out_poly_stride = J.out_stride ? J.out_stride : N;
     P.in_inner = J.in_inner ? J.in_inner : ~(size_t)0; P.in_outer_stride = J.in_outer_stride;
     P.out_inner = J.out_inner ? J.out_inner : ~(size_t)0; P.out_outer_stride = J.out_outer_stride;
@@ -343,6 +357,7 @@ void ntt_run(const NttJob& J, cudaStream_t st) {
         NttPass B = P;
         B.in = J.scratch; B.out = J.out;
         B.in_poly_stride = N; B.in_valid = N; B.in_inner = ~(size_t)0; B.in_outer_stride = 0;
+        B.pre_table = nullptr;
         B.log_m = log_n2; B.log_C = pick_c(log_n2); B.swz_q = pick_swz(B.log_m, B.log_C);
         unsigned C = 1u << B.log_C;
         B.tiles_per_poly = (unsigned)(n1 >> B.log_C);

@@ -23,11 +23,19 @@ struct NttJob {
     fr_t cs1, cs2;
     int has_scale = 0;
     fr_t scale;
+    // optional per-element pre-multiplier: polynomial p multiplies input element i by pre_table[(p % pre_count) * N + i]
+    // (coset evaluation on g_c * H: table row c holds g_c^i); with in_broadcast the `in_inner` polynomials of one group
+    // all read the same input polynomial (stride 0 inside the group)
+    const fr_t* pre_table = nullptr;
+    unsigned pre_count = 1;
+    int in_broadcast = 0;
 };
 
 void ntt_run(const NttJob& job, cudaStream_t st);
 size_t ntt_scratch_elems(unsigned log_n, size_t batch);
 const fr_t* ntt_twiddles(unsigned log_n, const fr_t& omega, cudaStream_t st);
+// d_out[i] = base^i for i < 2^log_count (device buffer)
+void fr_power_table(fr_t* d_out, unsigned log_count, const fr_t& base, cudaStream_t st);
 void ntt_clear_cache();
 
 // host-side Fr helpers (run the same generated limb code on the CPU)

@@ -130,7 +130,7 @@ struct ProverWs {
     DevBuf<fr_t> carries;
     ~ProverWs() { if (stream) cudaStreamDestroy(stream); }
     DevBuf<fr_t> adv, inst, z, randp, adv_ext, z_ext, h, hpoly, comb, hx, lx, tmp1, tmp2, scratch, evals, low;
-    DevBuf<fr_t> lk_in, lk_tab, lk_a, lk_s, lk_z, lk_ext, sort_a, sort_t;   // lookups: [B][L][n] (lk_ext: [B][L][3][en])
+    DevBuf<fr_t> lk_in, lk_tab, lk_a, lk_s, lk_z, lk_ext, sort_a, sort_t;   // lookups: [B][L][n] (lk_ext: [B][L][3][Qc*n])
     DevBuf<uint64_t> raw_la, raw_ls, raw_lz;
     DevBuf<int> d_error;
     DevBuf<uint64_t> raw_adv, raw_z;
@@ -150,6 +150,11 @@ struct PkEntry {
     CsDesc cs;
     uint64_t srs_handle = 0;
     unsigned k = 0, ek = 0, A = 0, F = 0, S = 0, P = 0, Q = 0, bf = 0, chunk = 0, L = 0;
+    // The quotient is evaluated on Qc = Q cosets g_c * H (g_c = zeta * ext_omega^c, H the size-n subgroup) instead of on
+    // all 2^(ek-k) cosets of halo2's extended domain: h has Q*n coefficients, so Q cosets determine it.  cn = Qc * n rows.
+    unsigned Qc = 0;
+    size_t cn = 0;
+    DevBuf<fr_t> coset_pows, coset_pows_inv, vinv;   // g_c^m [Qc][n], g_c^-m [Qc][n], inverse Vandermonde [Qc][Qc]
     DevBuf<uint32_t> lk_prog, lk_expr_off, lk_off;
     size_t n = 0, en = 0, ustart = 0, num_evals = 0, proof_len = 0;
     int rot_last = 0;
@@ -195,32 +200,21 @@ static void intt_n(PkEntry& pk, ProverWs& W, fr_t* p, size_t count, cudaStream_t
         ntt_run(J, st);
     }
 }
-// coeff_to_extended: groups x cols polynomials at in[(g*cols + c)*n] -> out[g*out_group_stride + c*en]
+// coefficients -> values on the Qc quotient cosets: groups x cols polynomials at in[(g*cols + c)*n] -> out[g*out_group_stride + c*cn],
+// each output column coset-major [Qc][n].  Every coset is one size-n NTT of a[m] * g_c^m (table pk.coset_pows).
 static void coset_ext(PkEntry& pk, ProverWs& W, const fr_t* in, fr_t* out, size_t groups, size_t cols, size_t out_group_stride, cudaStream_t st) {
-    const bool two = pk.ek > NTT_SINGLE_PASS_MAX_LOG;
-    size_t per = two ? std::max<size_t>(1, (SCRATCH_ELEMS >> pk.ek) / cols) : groups;
-    if (two) W.scratch.ensure((std::min(groups, per) * cols) << pk.ek);
+    const bool two = pk.k > NTT_SINGLE_PASS_MAX_LOG;
+    const size_t per_group = cols * pk.Qc;
+    size_t per = two ? std::max<size_t>(1, (SCRATCH_ELEMS >> pk.k) / per_group) : groups;
+    if (two) W.scratch.ensure((std::min(groups, per) * per_group) << pk.k);
     for (size_t off = 0; off < groups; off += per) {
         size_t g = std::min(per, groups - off);
         NttJob J;
         J.in = in + off * cols * pk.n; J.out = out + off * out_group_stride; J.scratch = W.scratch.p;
-        J.batch = g * cols; J.log_n = pk.ek; J.omega = pk.ext_omega;
-        J.in_stride = pk.n; J.in_valid = pk.n; J.out_stride = pk.en;
-        J.out_inner = cols; J.out_outer_stride = out_group_stride;
-        J.pre_coset = 1; J.cs1 = pk.zeta; J.cs2 = pk.zeta_inv;
-        ntt_run(J, st);
-    }
-}
-// extended_to_coeff on `count` contiguous extended polynomials, in place (no truncation: callers read the prefix)
-static void coset_intt(PkEntry& pk, ProverWs& W, fr_t* p, size_t count, cudaStream_t st) {
-    const bool two = pk.ek > NTT_SINGLE_PASS_MAX_LOG;
-    size_t per = two ? std::max<size_t>(1, SCRATCH_ELEMS >> pk.ek) : count;
-    if (two) W.scratch.ensure(std::min(count, per) << pk.ek);
-    for (size_t off = 0; off < count; off += per) {
-        NttJob J;
-        J.in = J.out = p + (off << pk.ek); J.scratch = W.scratch.p; J.batch = std::min(per, count - off); J.log_n = pk.ek;
-        J.omega = pk.ext_omega_inv; J.post_coset = 1; J.cs1 = pk.zeta_inv; J.cs2 = pk.zeta;
-        J.has_scale = 1; J.scale = pk.en_inv;
+        J.batch = g * per_group; J.log_n = pk.k; J.omega = pk.omega;
+        J.in_broadcast = 1; J.in_inner = pk.Qc; J.in_outer_stride = pk.n;
+        J.out_stride = pk.n; J.out_inner = per_group; J.out_outer_stride = out_group_stride;
+        J.pre_table = pk.coset_pows.p; J.pre_count = pk.Qc;
         ntt_run(J, st);
     }
 }
@@ -273,6 +267,7 @@ static std::unique_ptr<PkEntry> keygen(Context& C, uint64_t srs_handle, const ui
     ZK_REQUIRE(S.k == cs.k, "keygen: params.k != circuit k (downsize the params first)");
     pk.srs_handle = srs_handle;
     pk.k = cs.k; pk.n = cs.n(); pk.ek = cs.extended_k(); pk.en = (size_t)1 << pk.ek;
+    pk.Qc = cs.num_quotients(); pk.cn = (size_t)pk.Qc * pk.n;
     pk.A = cs.num_advice; pk.F = cs.num_fixed; pk.S = (unsigned)cs.perm_columns.size(); pk.P = cs.num_perm_sets(); pk.Q = cs.num_quotients();
     pk.L = (unsigned)cs.num_lookups();
     pk.bf = cs.blinding_factors(); pk.chunk = cs.chunk_len(); pk.ustart = cs.unusable_start(); pk.rot_last = cs.rotation_last();
@@ -285,9 +280,48 @@ static std::unique_ptr<PkEntry> keygen(Context& C, uint64_t srs_handle, const ui
     pk.zeta = fr_from_limbs(fr_consts::ZETA); pk.zeta_inv = fr_from_limbs(fr_consts::ZETA_INV);
     pk.plan.build(cs);
     cudaStream_t st = C.stream;
-    const size_t n = pk.n, en = pk.en;
+    const size_t n = pk.n, en = pk.cn;   // rows per coset-major column
     pk.omega_tw = ntt_twiddles(pk.k, pk.omega, st);
     pk.ext_tw = ntt_twiddles(pk.ek, pk.ext_omega, st);
+    // quotient cosets: power tables of g_c = zeta * ext_omega^c and the inverse Vandermonde matrix in G_c = g_c^n
+    {
+        const unsigned Qc = pk.Qc;
+        ZK_REQUIRE(Qc >= 1 && Qc <= 16 && ((size_t)Qc << pk.k) <= pk.en, "keygen: unsupported number of quotient pieces");
+        pk.coset_pows.alloc((size_t)Qc * n); pk.coset_pows_inv.alloc((size_t)Qc * n);
+        std::vector<fr_t> G(Qc);
+        fr_t g = pk.zeta;
+        for (unsigned c = 0; c < Qc; ++c) {
+            fr_power_table(pk.coset_pows.p + (size_t)c * n, pk.k, g, st);
+            fr_power_table(pk.coset_pows_inv.p + (size_t)c * n, pk.k, fe_inv(g), st);
+            G[c] = fr_pow_u64(g, n);
+            g = g * pk.ext_omega;
+        }
+        // Gauss-Jordan on [V | I], V[c][j] = G_c^j
+        const fr_t one = fe_one<FrTag>();
+        std::vector<std::vector<fr_t>> M(Qc, std::vector<fr_t>(2 * Qc, fr_t::zero()));
+        for (unsigned c = 0; c < Qc; ++c) {
+            fr_t p = one;
+            for (unsigned j = 0; j < Qc; ++j) { M[c][j] = p; p = p * G[c]; }
+            M[c][Qc + c] = one;
+        }
+        for (unsigned col = 0; col < Qc; ++col) {
+            unsigned piv = col;
+            while (piv < Qc && M[piv][col].is_zero()) ++piv;
+            ZK_REQUIRE(piv < Qc, "keygen: singular coset Vandermonde matrix");
+            std::swap(M[piv], M[col]);
+            fr_t inv = fe_inv(M[col][col]);
+            for (auto& v : M[col]) v = v * inv;
+            for (unsigned r = 0; r < Qc; ++r) {
+                if (r == col || M[r][col].is_zero()) continue;
+                fr_t f = M[r][col];
+                for (unsigned j = 0; j < 2 * Qc; ++j) M[r][j] = M[r][j] - f * M[col][j];
+            }
+        }
+        std::vector<fr_t> vinv((size_t)Qc * Qc);
+        for (unsigned j = 0; j < Qc; ++j) for (unsigned c = 0; c < Qc; ++c) vinv[j * Qc + c] = M[j][Qc + c];
+        upload(pk.vinv, vinv, st);
+        ZK_CUDA(cudaStreamSynchronize(st));
+    }
 
     auto commit_cols = [&](const fr_t* d_vals, size_t count, std::vector<g1_affine_t>& out) {
         out.resize(count);
@@ -421,13 +455,13 @@ static size_t default_batch(const PkEntry& pk) {
     if (const char* e = getenv("ZKGPU_PROVER_BATCH")) { long v = atol(e); if (v > 0) return (size_t)v; }
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    size_t per = ((size_t)(pk.A + 1 + pk.P + 1 + 3 * pk.L) * pk.en + (size_t)(pk.A + 2 * pk.P + 7 * pk.L + 8 + 3 * pk.plan.sets.size()) * pk.n) * sizeof(fr_t);
+    size_t per = ((size_t)(pk.A + 1 + pk.P + 1 + 3 * pk.L) * pk.cn + (size_t)(pk.A + 2 * pk.P + 7 * pk.L + 8 + 3 * pk.plan.sets.size()) * pk.n) * sizeof(fr_t);
     size_t B = (size_t)(free_b * 0.2) / std::max<size_t>(per, 1);
     return std::max<size_t>(1, std::min<size_t>(B, 128));
 }
 
 static void ensure_ws(PkEntry& pk, ProverWs& W, size_t B) {
-    const size_t n = pk.n, en = pk.en, ns = pk.plan.sets.size();
+    const size_t n = pk.n, en = pk.cn, ns = pk.plan.sets.size();
     W.B = std::max(W.B, B);
     W.adv.ensure(B * pk.A * n); W.inst.ensure(B * n); W.z.ensure(std::max<size_t>(1, B * pk.P * n)); W.randp.ensure(B * n);
     W.adv_ext.ensure(B * (pk.A + 1) * en); W.z_ext.ensure(std::max<size_t>(1, B * pk.P * en)); W.h.ensure(B * en);
@@ -455,7 +489,7 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
     const CsDesc& cs = pk.cs;
     if (!W.stream) ZK_CUDA(cudaStreamCreateWithFlags(&W.stream, cudaStreamNonBlocking));
     cudaStream_t st = W.stream;
-    const size_t n = pk.n, en = pk.en, A = pk.A, P = pk.P, Q = pk.Q, bf = pk.bf;
+    const size_t n = pk.n, en = pk.cn /* coset-major rows per column */, A = pk.A, P = pk.P, Q = pk.Q, bf = pk.bf;
     const size_t ns = pk.plan.sets.size();
     ensure_ws(pk, W, B);
     const fr_t one = fe_one<FrTag>();
@@ -620,9 +654,9 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
     push_challenges();
     trace_dev("advice_poly", W.adv.p, n, A, n, st);
     trace_dev("z_poly", W.z.p, n, P, n, st);
-    trace_dev("z_coset", W.z_ext.p, en, P, en, st);
-    trace_dev("advice_coset", W.adv_ext.p, en, A, en, st);
-    trace_dev("instance_coset", W.adv_ext.p + A * en, en, 1, en, st);
+    trace_dev("z_quotient_cosets", W.z_ext.p, en, P, en, st);
+    trace_dev("advice_quotient_cosets", W.adv_ext.p, en, A, en, st);
+    trace_dev("instance_quotient_cosets", W.adv_ext.p + A * en, en, 1, en, st);
 
     timer.lap(2);
     // ---- step 3: quotient ---------------------------------------------------------------------
@@ -634,12 +668,13 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
         ea.prog = pk.prog.p; ea.gate_off = pk.gate_off.p; ea.constants = pk.constants.p;
         ea.adv_q = pk.adv_q.p; ea.fix_q = pk.fix_q.p; ea.inst_q = pk.inst_q.p;
         ea.num_gates = (unsigned)cs.gates.size(); ea.A = pk.A; ea.S = pk.S; ea.chunk = pk.chunk; ea.P = pk.P; ea.k = pk.k; ea.ek = pk.ek;
-        ea.rotation_last = pk.rot_last; ea.zeta = pk.zeta;
+        ea.rotation_last = pk.rot_last; ea.zeta = pk.zeta; ea.Qc = pk.Qc;
         ea.lk_ext = W.lk_ext.p; ea.lk_ext_proof_stride = 3 * L * en; ea.lp = lookup_progs(pk);
         launch_eval_h(ea, W.h.p, B, st);
     }
-    trace_dev("h_evals", W.h.p, en, 1, en, st);
-    coset_intt(pk, W, W.h.p, B, st);
+    trace_dev("h_quotient_cosets", W.h.p, en, 1, en, st);
+    intt_n(pk, W, W.h.p, B * pk.Qc, st);
+    launch_coset_combine(W.h.p, pk.coset_pows_inv.p, pk.vinv.p, pk.Qc, pk.k, B, st);
     trace_dev("h_coeffs", W.h.p, Q * n, 1, en, st);
     commit(C, pk, W, 0, W.h.p, B * Q, Q, en, W.aff.p, st);
     {

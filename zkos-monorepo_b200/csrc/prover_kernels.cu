@@ -255,16 +255,20 @@ void launch_chacha_poly(const uint8_t* seeds, fr_t* out, size_t n, size_t B, cud
 // evaluate_h: quotient numerator on the extended coset, divided by the vanishing polynomial
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_eval_h(const EvalHArgs a, fr_t* h, size_t B) {
-    const size_t en = (size_t)1 << a.ek;
+    // Rows are coset-major: row i = c * n + r is the point g_c * omega^r, g_c = zeta * ext_omega^c, c < Qc.  `en` below is
+    // the number of rows per column (Qc * n), not the size of halo2's extended domain.
+    const size_t n = (size_t)1 << a.k;
+    const size_t en = (size_t)a.Qc << a.k;
     // blocks of one row range are adjacent across the B proofs, so the proving-key columns they share stay in L2
     const size_t b = blockIdx.x % B;
     const size_t i = (size_t)(blockIdx.x / B) * blockDim.x + threadIdx.x;
     if (i >= en) return;
     const size_t t = b * en + i;
-    const unsigned rs = a.ek - a.k;  // rotation scale shift
+    const unsigned rs = a.ek - a.k;
+    const size_t coset = i >> a.k, cbase = coset << a.k;
     const fr_t* adv = a.adv_ext + b * a.adv_ext_proof_stride;
     const fr_t y = fe_ldg(&a.ch[b].y);
-    auto rot = [&](int r) -> size_t { return (i + ((size_t)(long)r << rs)) & (en - 1); };
+    auto rot = [&](int r) -> size_t { return cbase | ((i + (size_t)(long)r) & (n - 1)); };
 
     auto fixed_at = [&](uint32_t q) { return fe_ldg(a.fixed_ext + (size_t)a.fix_q[2 * q] * en + rot(a.fix_q[2 * q + 1])); };
     auto advice_at = [&](uint32_t q) { return fe_load(adv + (size_t)a.adv_q[2 * q] * en + rot(a.adv_q[2 * q + 1])); };
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(128) k_eval_h(const EvalHArgs a, fr_t* h, size
         v = v * y + (sqr(zl) - zl) * fe_ldg(a.l_last + i);
         for (unsigned s = 1; s < a.P; ++s)
             v = v * y + (fe_load(z + (size_t)s * en + i) - fe_load(z + (size_t)(s - 1) * en + r_last)) * l0;
-        fr_t cur = beta * a.zeta * pow_from_tw(a.ext_tw, i, en >> 1);
+        fr_t cur = beta * a.zeta * pow_from_tw(a.ext_tw, ((i & (n - 1)) << rs) + coset, (size_t)1 << (a.ek - 1));
         const fr_t delta = fr_delta();
         const fr_t lact = fe_ldg(a.l_active + i);
         for (unsigned s = 0; s < a.P; ++s) {
@@ -326,13 +330,41 @@ __global__ void __launch_bounds__(128) k_eval_h(const EvalHArgs a, fr_t* h, size
             v = v * y + (a_minus_s * (pa - fe_load(ac + r_prev))) * lact;
         }
     }
-    v = v * fe_ldg(a.t_inv + (i & (((size_t)1 << rs) - 1)));
+    v = v * fe_ldg(a.t_inv + coset);
     fe_store(h + t, v);
 }
 void launch_eval_h(const EvalHArgs& a, fr_t* h, size_t B, cudaStream_t st) {
-    size_t total = B << a.ek;
+    size_t rows = (size_t)a.Qc << a.k;
     KtScope kt(KT_EVAL_H, st);
-    if (total) ZK_LAUNCH(k_eval_h, (unsigned)(ceil_div((size_t)1 << a.ek, 128) * B), 128, 0, st, a, h, B);
+    if (B) ZK_LAUNCH(k_eval_h, (unsigned)(ceil_div(rows, 128) * B), 128, 0, st, a, h, B);
+}
+
+template <int MAXQ>
+__global__ void __launch_bounds__(128) k_coset_combine(fr_t* hc, const fr_t* ginv, const fr_t* vinv, unsigned Qc, unsigned k, size_t B) {
+    const size_t n = (size_t)1 << k;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * n) return;
+    const size_t b = t >> k, m = t & (n - 1);
+    fr_t* base = hc + b * Qc * n + m;
+    fr_t d[MAXQ];
+#pragma unroll
+    for (unsigned c = 0; c < MAXQ; ++c)
+        if (c < Qc) d[c] = fe_load(base + c * n) * fe_ldg(ginv + c * n + m);
+    for (unsigned j = 0; j < Qc; ++j) {
+        fr_t acc = fr_t::zero();
+#pragma unroll
+        for (unsigned c = 0; c < MAXQ; ++c)
+            if (c < Qc) acc = acc + fe_ldg(vinv + j * Qc + c) * d[c];
+        fe_store(base + j * n, acc);
+    }
+}
+void launch_coset_combine(fr_t* hc, const fr_t* ginv, const fr_t* vinv, unsigned Qc, unsigned k, size_t B, cudaStream_t st) {
+    ZK_REQUIRE(Qc >= 1 && Qc <= 16, "coset combine: at most 16 quotient cosets");
+    size_t total = B << k;
+    KtScope kt(KT_EVAL_H, st);
+    if (!total) return;
+    if (Qc <= 8) ZK_LAUNCH(k_coset_combine<8>, ceil_div(total, 128), 128, 0, st, hc, ginv, vinv, Qc, k, B);
+    else ZK_LAUNCH(k_coset_combine<16>, ceil_div(total, 128), 128, 0, st, hc, ginv, vinv, Qc, k, B);
 }
 
 // ---------------------------------------------------------------------------------------------

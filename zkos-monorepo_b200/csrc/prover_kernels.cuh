@@ -67,12 +67,12 @@ void launch_lookup_num_den(const fr_t* comp_in, const fr_t* comp_tab, const fr_t
 
 struct EvalHArgs {
     // per-proof extended cosets
-    const fr_t* adv_ext; size_t adv_ext_proof_stride;  // [B][A+1][en], instance coset at column A
-    const fr_t* z_ext;   size_t z_ext_proof_stride;    // [B][P][en]
+    const fr_t* adv_ext; size_t adv_ext_proof_stride;  // [B][A+1][Qc*n], instance coset at column A
+    const fr_t* z_ext;   size_t z_ext_proof_stride;    // [B][P][Qc*n]
     // proving key
-    const fr_t* fixed_ext;   // [F][en]
-    const fr_t* sigma_ext;   // [S][en]
-    const fr_t* l0; const fr_t* l_last; const fr_t* l_active;  // [en]
+    const fr_t* fixed_ext;   // [F][Qc*n]
+    const fr_t* sigma_ext;   // [S][Qc*n]
+    const fr_t* l0; const fr_t* l_last; const fr_t* l_active;  // [Qc*n]
     const fr_t* t_inv;       // [2^(ek-k)]
     const fr_t* ext_tw;      // ext_omega^i, i < en/2
     const fr_t* delta_pows;  // unused by the kernel (delta is a constant) — kept for symmetry
@@ -85,14 +85,20 @@ struct EvalHArgs {
     const int32_t* adv_q;  // [num_advice_queries][2] = (column, rotation)
     const int32_t* fix_q;
     const int32_t* inst_q;
-    // lookups: extended cosets [B][L][3][en] in the order (z, permuted input, permuted table)
+    // lookups: extended cosets [B][L][3][Qc*n] in the order (z, permuted input, permuted table)
     const fr_t* lk_ext; size_t lk_ext_proof_stride;
     LookupProgs lp;
     unsigned num_gates, A, S, chunk, P, k, ek;
+    unsigned Qc;  // cosets of the size-n subgroup the quotient is evaluated on (= number of quotient pieces)
     int rotation_last;
     fr_t zeta;  // coset generator (Montgomery)
 };
-void launch_eval_h(const EvalHArgs& a, fr_t* h /*[B][en]*/, size_t B, cudaStream_t st);
+void launch_eval_h(const EvalHArgs& a, fr_t* h /*[B][Qc*n]*/, size_t B, cudaStream_t st);
+
+// Quotient pieces from its values on Qc cosets.  hc [B][Qc][n] holds, for coset c, the coefficients of h(g_c X) mod (X^n - 1)
+// (size-n iNTT of the coset values); overwritten in place with the pieces h_j, h(X) = sum_j X^(jn) h_j(X):
+//   h_j[m] = sum_c vinv[j*Qc + c] * ginv[c][m] * hc[c][m],   ginv[c][m] = g_c^-m,  vinv = inverse of V[c][j] = (g_c^n)^j
+void launch_coset_combine(fr_t* hc, const fr_t* ginv /*[Qc][n]*/, const fr_t* vinv /*[Qc*Qc]*/, unsigned Qc, unsigned k, size_t B, cudaStream_t st);
 
 struct EvalJob { const fr_t* poly; fr_t x; };
 // out[j] = poly_j(x_j) for polynomials of n = 2^k coefficients
