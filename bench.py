@@ -227,14 +227,15 @@ def main():
     L.zkgpu_kernel_timing(0)
     ksteps = 1
 
-    # ---- single-proof latency (the metric's second half): m = 1 through the same call, p50 of 21 -----
+    # ---- single-proof latency (the metric's second half): m = 1 through the same call, p50 of 64 -----
     lat = []
-    for i in range(24):
+    for i in range(68):
         t = time.perf_counter()
         pk.prove_batch_dev(d_adv.data_ptr(), inst[:1], seeds[:1], out=proofs[:pk.proof_len])
         lat.append(1e3 * (time.perf_counter() - t))
-    lat = sorted(lat[3:])
+    lat = sorted(lat[4:])
     p50_ms = lat[len(lat) // 2]
+    latency = {"calls": len(lat), "p10_ms": lat[len(lat) // 10], "p50_ms": p50_ms, "p90_ms": lat[(9 * len(lat)) // 10]}
 
     # ---- e2e: host buffers through the C ABI --------------------------------------------------------
     step_host()
@@ -328,7 +329,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "roofline_hbm": roof_hbm, "roofline_imad": roof_imad,
             "kernel_ms_per_step": {k_: round(v[0], 3) for k_, v in ktimes.items()}, "kernel_timed_step_ms": ms_ktimed,
-            "single_proof_p50_ms": p50_ms, "cpu_baseline": cpu_baseline,
+            "single_proof_p50_ms": p50_ms, "single_proof_latency": latency, "cpu_baseline": cpu_baseline,
         }), flush=True)
     if dist is not None:
         dist.barrier()

@@ -130,7 +130,7 @@ def test_unsatisfied_witness_rejected(tiny):
     # prover writes from the quotient commitments on depends on how many cosets it evaluates (halo2: all 2^(ek-k), truncated;
     # this library: num_quotients).  Everything before the quotient commitments is still byte-identical; the proof must not verify.
     want = po.prove(adv, pi, seed=1)
-    prefix = 64 * (shape.num_advice + 3 * len(shape.lookups) + shape.num_perm_sets + 1)
+    prefix = 64 * (shape.num_advice + 3 * shape.n_lookup + shape.num_perm_sets + 1)
     assert len(proof) == len(want) and proof[:prefix] == want[:prefix]
     assert not po.verify(proof, pi)
     assert not po.verify(want, pi)

@@ -17,6 +17,7 @@
 // formulas is handled, so the affine-normalised result is bit-exact against the CPU oracle.
 #include "msm.cuh"
 #include <mutex>
+#include <cstdlib>
 
 namespace zk {
 
@@ -515,7 +516,8 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
         if (!plan.precomp) ZK_LAUNCH(k_msm_combine, ceil_div(M, 64), 64, 0, st, ws.groups.p, D, M, d_out);
         return;
     }
-    unsigned Tmax = M * plan.G < 148 * 4 ? ZK_REDUCE_T_LAT : ZK_REDUCE_T;
+    static const unsigned reduce_t = [] { const char* e = getenv("ZKGPU_REDUCE_T"); unsigned v = e ? (unsigned)atoi(e) : 0; return (v == 32 || v == 64 || v == 128 || v == 256) ? v : (unsigned)ZK_REDUCE_T; }();
+    unsigned Tmax = M * plan.G < 148 * 4 ? ZK_REDUCE_T_LAT : reduce_t;
     unsigned T = plan.nb < Tmax ? plan.nb : Tmax;
     g1_xyzz_t* groups = plan.precomp ? d_out : ws.groups.p;
     static std::once_flag reduce_once;

@@ -27,6 +27,7 @@
 #include <map>
 #include <set>
 #include <cstdlib>
+#include <cstdio>
 #include <chrono>
 #include <thread>
 #include <exception>
@@ -128,7 +129,16 @@ struct ProverWs {
     cudaStream_t stream = nullptr;   // each worker owns a stream, an MSM workspace and the buffers below
     MsmWorkspace msm;
     DevBuf<fr_t> carries;
-    ~ProverWs() { if (stream) cudaStreamDestroy(stream); }
+    // host advice of the worker's NEXT sub-batch is uploaded on copy_stream into adv_next while the current one computes
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev = nullptr;
+    DevBuf<fr_t> adv_next;
+    const fr_t* prefetched_src = nullptr;
+    ~ProverWs() {
+        if (stream) cudaStreamDestroy(stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (copy_ev) cudaEventDestroy(copy_ev);
+    }
     DevBuf<fr_t> adv, inst, z, randp, adv_ext, z_ext, h, hpoly, comb, hx, lx, tmp1, tmp2, scratch, evals, low;
     DevBuf<fr_t> lk_in, lk_tab, lk_a, lk_s, lk_z, lk_ext, sort_a, sort_t;   // lookups: [B][L][n] (lk_ext: [B][L][3][Qc*n])
     DevBuf<uint64_t> raw_la, raw_ls, raw_lz;
@@ -235,6 +245,24 @@ static void commit(Context& C, PkEntry& pk, ProverWs& W, int basis, const fr_t* 
     }
 }
 
+// Upload of a sub-batch's advice columns (0.8 GB for 128 withdraw proofs).  The host->device copy engine is a FIFO shared
+// by every stream: a small pageable upload of either pipeline worker (challenges, RNG draws, job lists) issued while this
+// transfer is in flight blocks its host thread until the transfer ends.  When the caller's buffer is pinned (and therefore
+// device-mapped under UVA) a few CTAs pull it over PCIe instead, and the copy engine stays free for the small uploads.
+static void upload_advice(void* dst, const void* src, size_t bytes, cudaStream_t st, bool background) {
+    static const int mode = [] { const char* e = getenv("ZKGPU_H2D_PULL"); return e ? atoi(e) : 1; }();
+    static const unsigned ctas = [] { const char* e = getenv("ZKGPU_H2D_PULL_CTAS"); int v = e ? atoi(e) : 0; return (unsigned)(v > 0 ? v : 32); }();
+    // the copy engine is about twice as fast as SM reads over PCIe: a transfer nothing can hide (a worker's first sub-batch) uses it
+    if (mode && background && bytes % 16 == 0) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            launch_pull_from_host(dst, at.devicePointer, bytes, ctas, st);
+            return;
+        }
+        cudaGetLastError();   // unregistered host memory reports an error on some drivers: fall through to the copy engine
+    }
+    ZK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+}
 template <class T>
 static void h2d(T* dst, const std::vector<T>& src, cudaStream_t st) {
     if (!src.empty()) ZK_CUDA(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, st));
@@ -485,7 +513,7 @@ static void ensure_ws(PkEntry& pk, ProverWs& W, size_t B) {
 }
 
 static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* advice, bool advice_on_device, const fr_t* instance, size_t num_pi,
-                            size_t B, const uint64_t* seeds, uint8_t* proofs) {
+                            size_t B, const uint64_t* seeds, uint8_t* proofs, const fr_t* next_advice = nullptr, size_t next_B = 0) {
     const CsDesc& cs = pk.cs;
     if (!W.stream) ZK_CUDA(cudaStreamCreateWithFlags(&W.stream, cudaStreamNonBlocking));
     cudaStream_t st = W.stream;
@@ -531,7 +559,25 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
         rng.fill_bytes32(&cseeds[b * 32]);
     }
     if (advice_on_device) ZK_CUDA(cudaMemcpyAsync(W.adv.p, advice, B * A * n * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
-    else ZK_CUDA(cudaMemcpyAsync(W.adv.p, advice, B * A * n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+    else if (W.prefetched_src == advice) {
+        // uploaded while the previous sub-batch was computing: take the staging buffer
+        ZK_CUDA(cudaStreamWaitEvent(st, W.copy_ev, 0));
+        std::swap(W.adv.p, W.adv_next.p); std::swap(W.adv.n, W.adv_next.n);
+        W.prefetched_src = nullptr;
+    } else upload_advice(W.adv.p, advice, B * A * n * sizeof(fr_t), st, false);
+    // the next sub-batch's advice is pulled in the background once this one's own upload has landed (issued after the
+    // first commitments are back, so the two transfers do not share the PCIe link)
+    auto issue_prefetch = [&]() {
+        if (!next_advice || advice_on_device) return;
+        if (!W.copy_stream) {
+            ZK_CUDA(cudaStreamCreateWithFlags(&W.copy_stream, cudaStreamNonBlocking));
+            ZK_CUDA(cudaEventCreateWithFlags(&W.copy_ev, cudaEventDisableTiming));
+        }
+        W.adv_next.ensure(std::max(W.B, next_B) * A * n);
+        upload_advice(W.adv_next.p, next_advice, next_B * A * n * sizeof(fr_t), W.copy_stream, true);
+        ZK_CUDA(cudaEventRecord(W.copy_ev, W.copy_stream));
+        W.prefetched_src = next_advice;
+    };
     ZK_CUDA(cudaMemsetAsync(W.inst.p, 0, B * n * sizeof(fr_t), st));
     if (num_pi)
         ZK_CUDA(cudaMemcpy2DAsync(W.inst.p, n * sizeof(fr_t), instance, num_pi * sizeof(fr_t), num_pi * sizeof(fr_t), B, cudaMemcpyHostToDevice, st));
@@ -556,6 +602,7 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
     commit(C, pk, W, 1, W.adv.p, B * A, 0, 0, W.aff.p, st);
     {
         const g1_affine_t* pts = fetch_points(B * A);
+        issue_prefetch();
         for (size_t b = 0; b < B; ++b) {
             for (size_t c = 0; c < A; ++c) ps[b].tr.write_point(pts[b * A + c]);
             ps[b].theta = ps[b].tr.squeeze();
@@ -939,10 +986,13 @@ static void prove_batch(uint64_t handle, const uint64_t* advice, bool advice_on_
     const fr_t* inst = reinterpret_cast<const fr_t*>(instance);
     auto run = [&](unsigned w) {
         ZK_CUDA(cudaSetDevice(C.device));
+        pk.ws[w].prefetched_src = nullptr;
         for (size_t sb = w; sb < nsub; sb += workers) {
             size_t off = sb * Bmax, B = std::min(Bmax, m - off);
+            size_t nsb = sb + workers, noff = nsb * Bmax;
+            const fr_t* next = nsb < nsub ? adv + noff * pk.A * pk.n : nullptr;
             prove_sub_batch(C, pk, pk.ws[w], adv + off * pk.A * pk.n, advice_on_device, inst + off * num_pi, num_pi, B, seeds + off,
-                            proofs + off * proof_len);
+                            proofs + off * proof_len, next, next ? std::min(Bmax, m - noff) : 0);
         }
     };
     if (workers == 1) { run(0); return; }

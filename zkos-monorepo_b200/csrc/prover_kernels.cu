@@ -492,6 +492,24 @@ void launch_kate_div(const DivJob* jobs, size_t num_jobs, unsigned k, cudaStream
 }
 
 // ---------------------------------------------------------------------------------------------
+// upload from pinned (device-mapped) host memory by the SMs: leaves the host->device copy engine to the
+// small per-step uploads, which would otherwise queue behind an 800 MB transfer
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pull_from_host(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t count) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < count; i += 4 * stride) {
+        uint4 a = __ldcs(src + i), b = __ldcs(src + i + stride), c = __ldcs(src + i + 2 * stride), d = __ldcs(src + i + 3 * stride);
+        dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+    }
+    for (; i < count; i += stride) dst[i] = __ldcs(src + i);
+}
+void launch_pull_from_host(void* dst, const void* mapped_src, size_t bytes, unsigned ctas, cudaStream_t st) {
+    ZK_REQUIRE(bytes % 16 == 0, "pull_from_host: size must be a multiple of 16 bytes");
+    if (bytes) ZK_LAUNCH(k_pull_from_host, ctas, 256, 0, st, (uint4*)dst, (const uint4*)mapped_src, bytes / 16);
+}
+
+// ---------------------------------------------------------------------------------------------
 // keygen helpers
 // ---------------------------------------------------------------------------------------------
 __global__ void k_sigma_values(const uint32_t* map_col, const uint32_t* map_row, const fr_t* delta_pows, const fr_t* omega_tw,

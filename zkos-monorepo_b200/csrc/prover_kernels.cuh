@@ -113,6 +113,9 @@ void launch_sub_low(fr_t* const* polys, const fr_t* low /*[jobs][4]*/, size_t nu
 struct DivJob { const fr_t* in; fr_t* out; const fr_t* low; fr_t pt; };  // low: optional 4 coefficients subtracted from `in` on load
 void launch_kate_div(const DivJob* jobs, size_t num_jobs, unsigned k, cudaStream_t st);
 
+// dst (device) <- mapped_src (device-visible pointer of pinned host memory), copied by `ctas` CTAs instead of the copy engine
+void launch_pull_from_host(void* dst, const void* mapped_src, size_t bytes, unsigned ctas, cudaStream_t st);
+
 // sigma values for keygen: out[c][row] = delta^{map_col} * omega^{map_row}
 void launch_sigma_values(const uint32_t* map_col, const uint32_t* map_row, const fr_t* delta_pows, const fr_t* omega_tw, fr_t* out,
                          size_t S, unsigned k, cudaStream_t st);
