@@ -101,6 +101,19 @@ int zkgpu_fr_to_mont(const uint64_t* canonical, uint64_t* out, size_t n);
 int zkgpu_fr_from_mont(const uint64_t* mont, uint64_t* out, size_t n);
 int zkgpu_fr_random(uint64_t seed, uint64_t* out, size_t n);
 
+/* ---- Poseidon2 (t = 8, rate 7) and the note-tree Merkle path: witness-side hashing --------------------------------
+ * shielder_bindings::hash::poseidon_hash = hash_variable_length (/root/reference/crates/shielder_bindings/src/hash.rs:16-27,
+ * src/utils.rs:14-30): m hashes of `len` (1..7; anything else is an error, as upstream panics) field elements each, the same
+ * permutation as the on-chain Poseidon2T8Assembly (/root/reference/poseidon2-solidity/generate_t8.py).  inputs m x len x 4 u64,
+ * out m x 4 u64, Montgomery form like every other field buffer. */
+int zkgpu_poseidon2_hash_batch(const uint64_t* inputs, size_t len, size_t m, uint64_t* out);
+int zkgpu_poseidon2_hash_batch_dev(const void* d_inputs, size_t len, size_t m, void* d_out, void* stream);
+/* m Merkle paths in the layout of MerkleTree.getMerklePath without the trailing root
+ * (/root/reference/contracts/MerkleTree.sol:88-113; `vec_to_path`, shielder_bindings/src/utils.rs:36-41): height x 7 elements,
+ * leaf level first.  roots[i] = hash(top level); consistent[i] (may be NULL) = 1 iff every level contains the hash of the
+ * level below it, i.e. the path is one `_addNote` could have produced (:134-147). */
+int zkgpu_merkle_root_batch(const uint64_t* paths, size_t height, size_t m, uint64_t* roots, uint8_t* consistent);
+
 /* ---- device-resident variants (inputs already in HBM; `stream` is a cudaStream_t or NULL) ------
  * Used by the prover pipeline and by bench.py's kernel-only ("value") measurement. */
 int zkgpu_ntt_fr_batch_dev(void* d_a, const uint64_t omega[4], uint32_t log_n, size_t m, void* d_scratch, void* stream);

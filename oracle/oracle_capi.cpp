@@ -8,6 +8,7 @@
 #include "misc.hpp"
 #include "pairing.hpp"
 #include "plonk.hpp"
+#include "poseidon2.hpp"
 
 using namespace oracle;
 
@@ -23,6 +24,31 @@ static void stp(u64* p, const G1Affine& a) { st(p, a.x); st(p + 4, a.y); }
 extern "C" {
 
 const char* orc_last_error() { return g_err.c_str(); }
+
+// Poseidon2 t=8: m hashes of `len` (1..7) Mont-LE elements each
+int orc_poseidon2_hash(const u64* in, size_t len, size_t m, u64* out) {
+    ORC_TRY
+    const Poseidon2& P = Poseidon2::get();
+    std::vector<Fr> v(len);
+    for (size_t i = 0; i < m; ++i) {
+        for (size_t j = 0; j < len; ++j) v[j] = ld<Fr>(in + 4 * (i * len + j));
+        st(out + 4 * i, P.hash(v.data(), len));
+    }
+    ORC_CATCH
+}
+// m Merkle paths of height x 7 elements -> roots, consistency flags
+int orc_merkle_root(const u64* paths, size_t height, size_t m, u64* roots, uint8_t* consistent) {
+    ORC_TRY
+    const Poseidon2& P = Poseidon2::get();
+    std::vector<Fr> v(height * 7);
+    for (size_t i = 0; i < m; ++i) {
+        for (size_t j = 0; j < height * 7; ++j) v[j] = ld<Fr>(paths + 4 * (i * height * 7 + j));
+        bool ok = true;
+        st(roots + 4 * i, P.merkle_root(v.data(), height, &ok));
+        if (consistent) consistent[i] = ok ? 1 : 0;
+    }
+    ORC_CATCH
+}
 
 // op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 square(a), 5 neg(a); field: 0 Fr, 1 Fq; elementwise over n
 int orc_field_op(int field, int op, const u64* a, const u64* b, u64* out, size_t n) {

@@ -30,6 +30,10 @@ extern "C" {
     pub fn zkgpu_g1_sum_affine(points_affine: *const u64, n: usize, out_affine: *mut u64) -> c_int;
     pub fn zkgpu_g1_on_curve(points_affine: *const u64, n: usize, bad_count: *mut u64) -> c_int;
 
+    pub fn zkgpu_poseidon2_hash_batch(inputs: *const u64, len: usize, m: usize, out: *mut u64) -> c_int;
+    pub fn zkgpu_poseidon2_hash_batch_dev(d_inputs: *const c_void, len: usize, m: usize, d_out: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn zkgpu_merkle_root_batch(paths: *const u64, height: usize, m: usize, roots: *mut u64, consistent: *mut u8) -> c_int;
+
     pub fn zkgpu_pk_create(srs: u64, circuit_blob: *const u8, blob_len: usize, pk_out: *mut u64) -> c_int;
     pub fn zkgpu_pk_release(pk: u64) -> c_int;
     pub fn zkgpu_pk_info(pk: u64, info: *mut u64) -> c_int;

@@ -291,3 +291,22 @@ class PlonkOracle:
             lib().orc_plonk_free(self.h)
         except Exception:
             pass
+
+
+def poseidon2_hash(inputs):
+    """inputs [m][len][4] Mont-LE (len 1..7) -> [m][4]"""
+    inputs = np.ascontiguousarray(inputs, dtype=np.uint64)
+    m, ln = inputs.shape[0], inputs.shape[1]
+    out = np.empty((m, 4), dtype=np.uint64)
+    _chk(lib().orc_poseidon2_hash(_p(inputs), C.c_size_t(ln), C.c_size_t(m), _p(out)))
+    return out
+
+
+def merkle_root(paths):
+    """paths [m][height][7][4] Mont-LE -> (roots [m][4], consistent [m] bool)"""
+    paths = np.ascontiguousarray(paths, dtype=np.uint64)
+    m, height = paths.shape[0], paths.shape[1]
+    roots = np.empty((m, 4), dtype=np.uint64)
+    ok = np.empty(m, dtype=np.uint8)
+    _chk(lib().orc_merkle_root(_p(paths), C.c_size_t(height), C.c_size_t(m), _p(roots), _p(ok)))
+    return roots, ok.astype(bool)

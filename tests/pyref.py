@@ -90,3 +90,32 @@ ZETA = 0x30644e72e131a029048b6e193fd84104cc37a73fec2bc5e9b8ca0b2d36636f23
 
 def omega_for(k):
     return pow(ROOT_OF_UNITY, 1 << (28 - k), R_MOD)
+
+
+# ---- Poseidon2, t = 8 (plain-integer restatement of /root/reference/poseidon2-solidity/generate_t8.py) ----
+def _p2_params():
+    import json
+    import os
+    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "poseidon2_t8.json")))
+    return d, [int(c, 16) for c in d["round_constants"]], [int(x, 16) for x in d["diag"]]
+
+
+def poseidon2_t8(inputs, p=R_MOD):
+    """hash of 1..7 integers: zero-padded rate part, capacity element len * 2^64, output state[0]"""
+    d, Cs, D = _p2_params()
+    RF, RP = d["rounds_f"], d["rounds_p"]
+    s = [x % p for x in inputs] + [0] * (7 - len(inputs)) + [len(inputs) << 64]
+
+    def ext(s):
+        # generate_t8.py:480-516 written as the matrix it implements (M of the generator, :461-468)
+        return [sum(m * x for m, x in zip(row, s)) % p for row in d["M"]]
+
+    s = ext(s)
+    for r in range(RF + RP):
+        if RF // 2 <= r < RF // 2 + RP:
+            s[0] = pow(s[0] + Cs[8 * r], 7, p)
+            tot = sum(s) % p
+            s = [(D[i] * s[i] + tot) % p for i in range(8)]
+        else:
+            s = ext([pow(s[i] + Cs[8 * r + i], 7, p) for i in range(8)])
+    return s[0]

@@ -290,3 +290,48 @@ def set_trace(fn):
     cb = TRACE_FN(fn) if fn is not None else C.cast(None, TRACE_FN)
     lib().zkgpu_set_trace(cb)
     return cb
+
+
+# ---- Poseidon2 / note-tree Merkle path (witness-side hashing on the GPU) -----------------------------------
+POSEIDON_RATE = 7       # shielder_circuits::consts::POSEIDON_RATE
+ARITY, NOTE_TREE_HEIGHT = 7, 13   # /root/reference/crates/shielder-setup/lib.rs:4-5, contracts/MerkleTree.sol:17-18
+
+
+def poseidon_rate():
+    """shielder_bindings::hash::poseidon_rate (/root/reference/crates/shielder_bindings/src/hash.rs:10-14)"""
+    return POSEIDON_RATE
+
+
+def poseidon2_hash(inputs):
+    """`hash_variable_length` over a batch: inputs (m, len, 4) Montgomery limbs with 1 <= len <= 7 -> (m, 4)."""
+    inputs = _u64(inputs)
+    if inputs.ndim != 3 or inputs.shape[2] != 4:
+        raise ValueError("inputs must have shape (m, len, 4)")
+    m, ln = inputs.shape[0], inputs.shape[1]
+    out = np.empty((m, 4), dtype=np.uint64)
+    _chk(lib().zkgpu_poseidon2_hash_batch(_p(inputs), C.c_size_t(ln), C.c_size_t(m), _p(out)))
+    return out
+
+
+def poseidon_hash(inputs):
+    """shielder_bindings::hash::poseidon_hash (hash.rs:16-27): concatenated canonical little-endian 32-byte field
+    elements in, one such word out.  A length that is not a multiple of 32 panics upstream -> ValueError."""
+    from . import conversions as cv
+    inputs = bytes(inputs)
+    if len(inputs) % cv.FR_SIZE != 0:
+        raise ValueError("Input length must be divisible by F::size()")
+    elems = np.stack([cv.vec_to_f(inputs[o:o + cv.FR_SIZE]) for o in range(0, len(inputs), cv.FR_SIZE)]) if inputs else np.zeros((0, 4), np.uint64)
+    return cv.field_to_bytes(poseidon2_hash(elems[None])[0])
+
+
+def merkle_root(paths):
+    """paths (m, height, 7, 4) as `vec_to_path` decodes them -> (roots (m, 4), consistent (m,) bool): the root every
+    path hashes to and whether each level contains the hash of the level below (MerkleTree.sol:121-152)."""
+    paths = _u64(paths)
+    if paths.ndim != 4 or paths.shape[2] != ARITY or paths.shape[3] != 4:
+        raise ValueError("paths must have shape (m, height, 7, 4)")
+    m, height = paths.shape[0], paths.shape[1]
+    roots = np.empty((m, 4), dtype=np.uint64)
+    ok = np.empty(m, dtype=np.uint8)
+    _chk(lib().zkgpu_merkle_root_batch(_p(paths), C.c_size_t(height), C.c_size_t(m), _p(roots), _p(ok)))
+    return roots, ok.astype(bool)
