@@ -39,11 +39,11 @@ int hl_perm_mapping(const uint8_t* blob, size_t len, uint32_t* out_col, uint32_t
 }
 }
 extern "C" {
-// field inversion: binary extended Euclid (fe_inv) vs Fermat (fe_inv_pow); field 0 = Fr, 1 = Fq
+// field inversion: which 0 = fe_inv (uniform-flow binary GCD), 1 = Fermat (fe_inv_pow), 2 = binary extended Euclid; field 0 = Fr, 1 = Fq
 void hl_inv(int field, int which, const uint32_t* a, uint32_t* out, size_t n) {
     for (size_t i = 0; i < n; ++i) {
-        if (field == 0) { fr_t x; memcpy(x.l, a + 8 * i, 32); fr_t r = which ? fe_inv_pow(x) : fe_inv(x); memcpy(out + 8 * i, r.l, 32); }
-        else { fq_t x; memcpy(x.l, a + 8 * i, 32); fq_t r = which ? fe_inv_pow(x) : fe_inv(x); memcpy(out + 8 * i, r.l, 32); }
+        if (field == 0) { fr_t x; memcpy(x.l, a + 8 * i, 32); fr_t r = which == 1 ? fe_inv_pow(x) : which == 2 ? fe_inv_euclid(x) : fe_inv(x); memcpy(out + 8 * i, r.l, 32); }
+        else { fq_t x; memcpy(x.l, a + 8 * i, 32); fq_t r = which == 1 ? fe_inv_pow(x) : which == 2 ? fe_inv_euclid(x) : fe_inv(x); memcpy(out + 8 * i, r.l, 32); }
     }
 }
 }

@@ -144,12 +144,18 @@ def test_permutation_assembly(hl):
 def test_binary_inversion(hl, field, p):
     """fe_inv (binary extended Euclid) == a^(p-2) == big-int inverse, in Montgomery form; 0 -> 0."""
     rng = np.random.default_rng(5 + field)
-    vals = [0, 1, 2, p - 1, p - 2, (p + 1) // 2, 1 << 253, (1 << 32) - 1] + [int.from_bytes(rng.bytes(40), "little") % p for _ in range(300)]
+    vals = [0, 1, 2, 3, p - 1, p - 2, (p + 1) // 2, (p - 1) // 2, 1 << 253, (1 << 32) - 1, 1 << 32, (1 << 64) - 1, 1 << 15, (1 << 15) - 1, 1 << 31,
+            (1 << 254) % p, pow(2, -1, p), pow(2, -15, p), pow(2, -510, p), pow(3, -1, p)] \
+        + [pow(2, e, p) for e in range(0, 254, 7)] + [(p - pow(2, e, p)) % p for e in range(0, 254, 11)] \
+        + [int.from_bytes(rng.bytes(40), "little") % p for _ in range(3000)] + [int.from_bytes(rng.bytes(k), "little") for k in range(1, 31)]
     mont = P.int_to_limbs([v * P.MONT_R % p for v in vals])
     a32 = mont.view(np.uint32)
     got = np.empty_like(a32); ref = np.empty_like(a32)
     hl.hl_inv(field, 0, a32.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), C.c_size_t(len(vals)))
     hl.hl_inv(field, 1, a32.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p), C.c_size_t(len(vals)))
     assert np.array_equal(got, ref)
+    euc = np.empty_like(a32)
+    hl.hl_inv(field, 2, a32.ctypes.data_as(C.c_void_p), euc.ctypes.data_as(C.c_void_p), C.c_size_t(len(vals)))
+    assert np.array_equal(euc, ref)
     want = [(pow(v, -1, p) * P.MONT_R % p) if v else 0 for v in vals]
     assert P.limbs_to_int(got.view(np.uint64)) == want
