@@ -498,7 +498,8 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
     {
         KtScope kt(KT_MSM_BUCKETS, st);
         ZK_CUDA(cudaMemsetAsync(ws.heavy_count.p, 0, sizeof(uint32_t), st));
-        if (M * K < (size_t)148 * 2048)   // latency regime: too few buckets to fill the GPU with one thread each
+        static const size_t split_below = [] { const char* e = getenv("ZKGPU_SPLIT_BELOW"); long v = e ? atol(e) : -1; return v >= 0 ? (size_t)v : (size_t)148 * 512; }();   // measured: 24 MSMs x 4096 buckets already run faster one thread per bucket
+        if (M * K < split_below)   // latency regime: too few buckets to fill the GPU with one thread each
             ZK_LAUNCH(k_msm_buckets_split, ceil_div(M * K * ZK_SPLIT, 128), 128, 0, st, d_bases, ws.offsets.p, ws.entries.p, D, M, ws.buckets.p,
                       ws.heavy_count.p, ws.heavy_list.p);
         else
