@@ -146,6 +146,10 @@ int zkgpu_pk_vk(uint64_t pk, uint64_t* fixed_commitments, uint64_t* perm_commitm
  * `transcript.finalize()` returns (/root/reference/crates/halo2-verifier/src/lib/verifier_contract.rs:14-20). */
 int zkgpu_prove_batch(uint64_t pk, const uint64_t* advice, const uint64_t* instance, size_t num_instance, size_t m,
                       const uint64_t* rng_seeds, uint8_t* proofs_out, size_t proof_len);
+/* halo2's vanishing prover draws the random polynomial in chunks of n / rayon::current_num_threads() coefficients, each from its
+ * own ChaCha20 stream seeded from the proof's rng, so proof bytes depend on the host's rayon thread count.  Tell the
+ * library the thread count of the host it replaces (default 1 = a single stream, the `multicore` feature off / RAYON_NUM_THREADS=1). */
+int zkgpu_set_rayon_threads(unsigned num_threads);
 /* same with the advice columns already resident in HBM */
 int zkgpu_prove_batch_dev(uint64_t pk, const void* d_advice, const uint64_t* instance, size_t num_instance, size_t m,
                           const uint64_t* rng_seeds, uint8_t* proofs_out, size_t proof_len);

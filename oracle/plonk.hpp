@@ -436,6 +436,9 @@ struct ProverStats {
     std::function<void(const char*, const Fr*, size_t)> trace;
 };
 
+// rayon::current_num_threads() of the prover being restated (affects only the chunking of the vanishing argument's random polynomial)
+static unsigned g_rayon_threads = 1;
+
 static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const ProvingKey& pk,
                                                 std::vector<std::vector<Fr>> advice,  // num_advice x n, assigned cells
                                                 const std::vector<Fr>& instance, RngCore& rng, ProverStats* stats = nullptr) {
@@ -592,12 +595,24 @@ static inline std::vector<uint8_t> create_proof(const ParamsKZG& params, const P
     }
 
     lap("lookup z");
-    // vanishing argument: random polynomial (single-thread ChaCha20 stream)
+    // vanishing argument: random polynomial.  halo2 v0.3.0 vanishing/prover.rs fills it in chunks of n / num_threads
+    // coefficients (num_threads = rayon::current_num_threads(); one more, shorter chunk when num_threads does not divide n),
+    // each chunk from its own ChaCha20Rng whose 32-byte seed is drawn from the main rng, in chunk order [UPSTREAM-MEMORY,
+    // SURVEY Appendix A / H3].  g_rayon_threads = 1 is the single-stream case (the `multicore` feature off).
     std::vector<Fr> random_poly(n);
     {
-        uint8_t seed[32]; rng.fill_bytes(seed, 32);
-        ChaCha20Rng crng(seed);
-        for (auto& v : random_poly) v = random_field<Fr>(crng);
+        const size_t T = g_rayon_threads ? g_rayon_threads : 1;
+        const size_t chunk = std::max<size_t>(1, n / T);
+        std::vector<uint8_t> chunk_seeds_tmp;
+        for (size_t lo = 0; lo < n; lo += chunk) {
+            uint8_t seed[32]; rng.fill_bytes(seed, 32);
+            chunk_seeds_tmp.insert(chunk_seeds_tmp.end(), seed, seed + 32);
+        }
+        size_t ci = 0;
+        for (size_t lo = 0; lo < n; lo += chunk, ++ci) {
+            ChaCha20Rng crng(&chunk_seeds_tmp[32 * ci]);
+            for (size_t i = lo; i < std::min(n, lo + chunk); ++i) random_poly[i] = random_field<Fr>(crng);
+        }
         (void)random_field<Fr>(rng);  // Blind
         trace("random_poly", random_poly);
         tr.write_point(params.commit(random_poly)); st.msms++;

@@ -40,6 +40,7 @@ extern "C" {
     pub fn zkgpu_pk_vk(pk: u64, fixed_commitments: *mut u64, perm_commitments: *mut u64, digest: *mut u64) -> c_int;
     pub fn zkgpu_prove_batch(pk: u64, advice: *const u64, instance: *const u64, num_instance: usize, m: usize,
                              rng_seeds: *const u64, proofs_out: *mut u8, proof_len: usize) -> c_int;
+    pub fn zkgpu_set_rayon_threads(num_threads: u32) -> c_int;
     pub fn zkgpu_prove_batch_dev(pk: u64, d_advice: *const c_void, instance: *const u64, num_instance: usize, m: usize,
                                  rng_seeds: *const u64, proofs_out: *mut u8, proof_len: usize) -> c_int;
 }

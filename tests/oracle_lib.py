@@ -310,3 +310,8 @@ def merkle_root(paths):
     ok = np.empty(m, dtype=np.uint8)
     _chk(lib().orc_merkle_root(_p(paths), C.c_size_t(height), C.c_size_t(m), _p(roots), _p(ok)))
     return roots, ok.astype(bool)
+
+
+def set_rayon_threads(t):
+    """rayon thread count emulated by the oracle prover's vanishing argument (default 1)"""
+    lib().orc_plonk_set_rayon_threads(C.c_uint(int(t)))

@@ -301,6 +301,24 @@ def test_two_pipeline_workers_and_ragged_sub_batches(tiny, monkeypatch):
     assert out.tobytes() == b"".join(proofs)
 
 
+def test_rayon_thread_count_chunks_the_random_polynomial(tiny):
+    """halo2's vanishing prover seeds one ChaCha20 stream per chunk of n / rayon::current_num_threads() coefficients, so the proof
+    bytes depend on the host's thread count: with the same setting on both sides the GPU proofs equal the CPU prover's
+    for thread counts that do and do not divide n, differ from the single-stream proof, and verify."""
+    shape, circ, po, params, pk = tiny
+    adv, pi = circ.witness(11)
+    base = pk.prove(adv, pi, 5)
+    try:
+        for t in (2, 8, 24, shape.n, 3 * shape.n):
+            zkgpu.set_rayon_threads(t); O.set_rayon_threads(t)
+            got = pk.prove(adv, pi, 5)
+            assert got == po.prove(adv, pi, seed=5), t
+            assert got != base and po.verify(got, pi)
+    finally:
+        zkgpu.set_rayon_threads(1); O.set_rayon_threads(1)
+    assert pk.prove(adv, pi, 5) == base
+
+
 def test_concurrent_api_callers_and_reinit(tiny):
     """The reference's hosts call the prover from arbitrary threads (tokio tasks, rayon workers): concurrent calls into
     the C ABI serialise on the library's context and stay correct; shutdown + init gives a working library again."""
@@ -336,3 +354,4 @@ def test_concurrent_api_callers_and_reinit(tiny):
     assert k2.prove(wits[0][0], wits[0][1], 700) == got[0]
     k2.release(); p2.release()
     pk.handle = 0; params.handle = 0                   # the module fixture's handles died with the shutdown
+

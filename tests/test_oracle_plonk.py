@@ -125,3 +125,25 @@ def test_batch_verification(setup):
     assert not ok
     wrong = inst.copy(); wrong[2, 0] = O.OracleBackend.const(7)
     assert po.verify_batch(proofs, wrong, threads=4)[0] is False
+
+
+def test_rayon_thread_count_changes_only_the_random_polynomial(setup):
+    """SURVEY H3: the vanishing argument's random polynomial is drawn in chunks of n / rayon::current_num_threads()
+    coefficients, one ChaCha20 stream per chunk.  The proof stays valid for every thread count, is deterministic per count,
+    and equals the single-stream proof only when there is a single chunk."""
+    shape, circ, po = setup
+    adv, pi = circ.witness(4)
+    base = po.prove(adv, pi, seed=9)
+    try:
+        seen = {base}
+        for t in (2, 8, 24, shape.n):
+            O.set_rayon_threads(t)
+            p1, p2 = po.prove(adv, pi, seed=9), po.prove(adv, pi, seed=9)
+            assert p1 == p2 and po.verify(p1, pi)
+            # the advice commitments (before the vanishing argument) do not depend on the thread count
+            assert p1[:64 * shape.num_advice] == base[:64 * shape.num_advice]
+            seen.add(p1)
+        assert len(seen) == 5
+    finally:
+        O.set_rayon_threads(1)
+    assert po.prove(adv, pi, seed=9) == base

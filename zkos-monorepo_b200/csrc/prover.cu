@@ -25,6 +25,7 @@
 #include "plonk_types.hpp"
 #include "host_util.hpp"
 #include <map>
+#include <atomic>
 #include <set>
 #include <cstdlib>
 #include <cstdio>
@@ -181,6 +182,11 @@ struct PkEntry {
 };
 
 static std::map<uint64_t, std::unique_ptr<PkEntry>> g_pks;
+// rayon::current_num_threads() of the host being replaced: halo2's vanishing prover fills the random polynomial in chunks of
+// n / num_threads coefficients, one ChaCha20 stream (seeded from the proof's main rng, in chunk order) per chunk, so the proof bytes
+// depend on it.  1 = one stream (the `multicore` feature off); set with zkgpu_set_rayon_threads.
+static std::atomic<unsigned> g_rayon_threads{1};
+static size_t vanishing_chunk(size_t n) { unsigned t = g_rayon_threads.load(); return std::max<size_t>(1, n / (t ? t : 1)); }
 static uint64_t g_next_pk = 1;
 void prover_release_all() { g_pks.clear(); }
 
@@ -505,7 +511,7 @@ static void ensure_ws(PkEntry& pk, ProverWs& W, size_t B) {
     }
     W.d_error.ensure(1);
     W.raw_adv.ensure(std::max<size_t>(1, B * pk.A * (pk.bf + 1) * 8)); W.raw_z.ensure(std::max<size_t>(1, B * pk.P * pk.bf * 8));
-    W.seeds.ensure(B * 32); W.ch.ensure(B);
+    W.seeds.ensure(B * 32 * ((pk.n + vanishing_chunk(pk.n) - 1) / vanishing_chunk(pk.n))); W.ch.ensure(B);
     size_t max_pts = B * std::max<size_t>(std::max<size_t>(pk.A, pk.P + pk.L + 1), std::max<size_t>(pk.Q, 2 * pk.L + 1));
     W.aff.ensure(max_pts);
     W.h_aff.ensure(max_pts * sizeof(g1_affine_t)); W.h_evals.ensure(B * (pk.num_evals + 1) * sizeof(fr_t));
@@ -529,7 +535,8 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
     const size_t L = pk.L;
     std::vector<uint64_t> raw_adv(B * A * (bf + 1) * 8), raw_z(B * P * bf * 8);
     std::vector<uint64_t> raw_la(B * L * (bf + 1) * 8), raw_ls(B * L * (bf + 1) * 8), raw_lz(B * L * bf * 8);
-    std::vector<uint8_t> cseeds(B * 32);
+    const size_t vchunk = vanishing_chunk(n), vnch = (n + vchunk - 1) / vchunk;
+    std::vector<uint8_t> cseeds(B * vnch * 32);
     for (size_t b = 0; b < B; ++b) {
         ps.emplace_back(proofs + b * pk.proof_len);
         ProofState& p = ps.back();
@@ -556,7 +563,7 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
             rng.skip_wide();
         }
         // vanishing: ChaCha20 seed for the random polynomial, its Blind; quotient piece Blinds follow (unused)
-        rng.fill_bytes32(&cseeds[b * 32]);
+        for (size_t c = 0; c < vnch; ++c) rng.fill_bytes32(&cseeds[(b * vnch + c) * 32]);
     }
     if (advice_on_device) ZK_CUDA(cudaMemcpyAsync(W.adv.p, advice, B * A * n * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
     else if (W.prefetched_src == advice) {
@@ -665,7 +672,7 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
         trace_dev("lookup_z", W.lk_z.p, n, L, n, st);
         commit(C, pk, W, 1, W.lk_z.p, B * L, 0, 0, W.aff.p + B * P, st);
     }
-    launch_chacha_poly(W.seeds.p, W.randp.p, n, B, st);
+    launch_chacha_poly(W.seeds.p, W.randp.p, n, B, vchunk, vnch, st);
     trace_dev("random_poly", W.randp.p, n, 1, n, st);
     commit(C, pk, W, 0, W.randp.p, B, 0, 0, W.aff.p + B * (P + L), st);
     ZK_CUDA(cudaMemcpyAsync(W.h_aff.p, W.aff.p, B * (P + L + 1) * sizeof(g1_affine_t), cudaMemcpyDeviceToHost, st));
@@ -1020,6 +1027,12 @@ void zkgpu_prover_step_seconds(double out[8], int reset) {
     for (int i = 0; i < 8; ++i) { out[i] = g_step_s[i]; if (reset) g_step_s[i] = 0; }
 }
 void zkgpu_set_trace(void (*fn)(const char*, const void*, size_t)) { g_trace = fn; }
+int zkgpu_set_rayon_threads(unsigned num_threads) {
+    API_BEGIN
+    ZK_REQUIRE(num_threads >= 1 && num_threads <= 65536, "rayon thread count out of range");
+    g_rayon_threads.store(num_threads);
+    API_END
+}
 
 int zkgpu_pk_create(uint64_t srs, const uint8_t* circuit_blob, size_t blob_len, uint64_t* pk_out) {
     API_BEGIN

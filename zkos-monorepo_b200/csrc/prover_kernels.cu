@@ -226,11 +226,14 @@ __device__ __forceinline__ uint32_t rotl32(uint32_t x, int n) { return (x << n) 
 #define ZK_QR(a, b, c, d) \
     x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 12); \
     x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 7);
-__global__ void k_chacha_poly(const uint8_t* seeds, fr_t* out, size_t n, size_t B) {
+__global__ void k_chacha_poly(const uint8_t* seeds, fr_t* out, size_t n, size_t B, size_t chunk, size_t nchunks) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * n) return;
     size_t b = t / n, i = t - b * n;
-    const uint32_t* key = reinterpret_cast<const uint32_t*>(seeds + 32 * b);
+    // coefficient i belongs to chunk i / chunk and is the (i % chunk)-th draw of that chunk's stream
+    const size_t ci = i / chunk;
+    i -= ci * chunk;
+    const uint32_t* key = reinterpret_cast<const uint32_t*>(seeds + 32 * (b * nchunks + ci));
     uint32_t s[16], x[16];
     s[0] = 0x61707865; s[1] = 0x3320646e; s[2] = 0x79622d32; s[3] = 0x6b206574;
 #pragma unroll
@@ -247,8 +250,8 @@ __global__ void k_chacha_poly(const uint8_t* seeds, fr_t* out, size_t n, size_t 
     for (int j = 0; j < 8; ++j) w[j] = (uint64_t)(x[2 * j] + s[2 * j]) | ((uint64_t)(x[2 * j + 1] + s[2 * j + 1]) << 32);
     fe_store(out + t, fr_from_wide(w));
 }
-void launch_chacha_poly(const uint8_t* seeds, fr_t* out, size_t n, size_t B, cudaStream_t st) {
-    if (B * n) ZK_LAUNCH(k_chacha_poly, ceil_div(B * n, 128), 128, 0, st, seeds, out, n, B);
+void launch_chacha_poly(const uint8_t* seeds, fr_t* out, size_t n, size_t B, size_t chunk, size_t nchunks, cudaStream_t st) {
+    if (B * n) ZK_LAUNCH(k_chacha_poly, ceil_div(B * n, 128), 128, 0, st, seeds, out, n, B, chunk, nchunks);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -35,8 +35,9 @@ void launch_perm_scan(const fr_t* num, const fr_t* den_inv, fr_t* z, unsigned k,
 // chain the sets (z_s *= prod_{t<s} z_t[u]) and overwrite the last bf rows with blinding values
 void launch_perm_finalize(fr_t* z, fr_t* carries /*[B][P] scratch*/, unsigned k, unsigned P, unsigned bf, const uint64_t* raw_wide /*[B][P][bf] x 8 u64*/, size_t B, cudaStream_t st);
 
-// random polynomial of the vanishing argument: coefficient i of proof b = Fr::random of ChaCha20(seed_b) block i
-void launch_chacha_poly(const uint8_t* seeds /*[B][32]*/, fr_t* out /*[B][n]*/, size_t n, size_t B, cudaStream_t st);
+// random polynomial of the vanishing argument, filled in chunks of `chunk` coefficients as halo2's vanishing prover does with
+// rayon: coefficient i of proof b = Fr::random of ChaCha20(seed[b][i / chunk]) block i % chunk
+void launch_chacha_poly(const uint8_t* seeds /*[B][nchunks][32]*/, fr_t* out /*[B][n]*/, size_t n, size_t B, size_t chunk, size_t nchunks, cudaStream_t st);
 
 // ---- lookup arguments (halo2 lookup/prover.rs) ------------------------------------------------------------
 // Expression programs of all lookups, flattened: lookup l owns expressions [lk_off[l], lk_off[l+1]) — first half

@@ -284,6 +284,11 @@ class ProvingKey:
 TRACE_FN = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p, C.c_size_t)
 
 
+def set_rayon_threads(num_threads):
+    """rayon::current_num_threads() of the host being replaced (chunking of the vanishing argument's random polynomial)."""
+    _chk(lib().zkgpu_set_rayon_threads(C.c_uint(int(num_threads))))
+
+
 def set_trace(fn):
     """fn(name: bytes, data_ptr, nbytes) per prover stage of proof 0, or None to disable.  Keep the returned
     object alive while tracing."""
