@@ -286,6 +286,17 @@ def main():
     roof_hbm["frac"] = roof_hbm["achieved"] / roof_hbm["peak"] if roof_hbm["achieved"] else None
     roofline = dict(roof_hbm if dom == "ntt_tile" else roof_imad)
     roofline["dominant_class"] = dom
+    # ---- whole-proof bound: field products of the MSMs and transforms at the IMAD ceiling vs transform bytes at HBM peak
+    nb = 1 << (c_win - 1)
+    k_log = shape.k
+    mul_msm = msm_per_proof * (n * W_win * 10 + 2 * nb * 14)
+    mul_ntt = shape.num_ntt * (n // 2) * k_log + (shape.num_ext_ntt - 1) * shape.num_quotients * ((n // 2) * k_log + n) + shape.num_quotients * (n // 2) * k_log
+    imad_bound = fmul_peak * 1e9 / (mul_msm + mul_ntt)
+    hbm_bound = hbm_peak * 1e9 / ntt_bytes_proof
+    proof_bound = {"msm_fieldmul_per_proof": mul_msm, "ntt_fieldmul_per_proof": mul_ntt, "ntt_bytes_per_proof": ntt_bytes_proof,
+                   "imad_bound_proofs_per_s": imad_bound, "hbm_bound_proofs_per_s": hbm_bound, "bound_proofs_per_s": min(imad_bound, hbm_bound),
+                   "achieved_frac_per_gpu": (value / world) / min(imad_bound, hbm_bound),
+                   "note": "MSM (bucket additions + bucket reduction) and NTT products only; quotient evaluation, grand products and openings are extra work the bound ignores"}
 
     # ---- CPU baseline + byte parity of a sample (rank 0, N = 1 only) ----------------------------------
     cpu_baseline = None
@@ -328,7 +339,7 @@ def main():
                        "l2": "inputs larger than L2 (%.1f GB of advice per step)" % (M * A * n * 32 / 1e9), "parallelism": "dp%d, no collective" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "roofline_hbm": roof_hbm, "roofline_imad": roof_imad,
-            "kernel_ms_per_step": {k_: round(v[0], 3) for k_, v in ktimes.items()}, "kernel_timed_step_ms": ms_ktimed,
+            "proof_bound": proof_bound, "kernel_ms_per_step": {k_: round(v[0], 3) for k_, v in ktimes.items()}, "kernel_timed_step_ms": ms_ktimed,
             "single_proof_p50_ms": p50_ms, "single_proof_latency": latency, "cpu_baseline": cpu_baseline,
         }), flush=True)
     if dist is not None:
