@@ -169,7 +169,7 @@ struct PkEntry {
     DevBuf<uint32_t> lk_prog, lk_expr_off, lk_off;
     size_t n = 0, en = 0, ustart = 0, num_evals = 0, proof_len = 0;
     int rot_last = 0;
-    fr_t omega, omega_inv, ext_omega, ext_omega_inv, n_inv, en_inv, zeta, zeta_inv, digest;
+    fr_t omega, omega_inv, ext_omega, n_inv, zeta, digest;
     DevBuf<fr_t> fixed_vals, fixed_polys, fixed_ext, sigma_vals, sigma_polys, sigma_ext, l0, l_last, l_active, t_inv, delta_pows, constants;
     DevBuf<ColSrc> cols;
     DevBuf<uint32_t> prog, gate_off;
@@ -309,9 +309,9 @@ static std::unique_ptr<PkEntry> keygen(Context& C, uint64_t srs_handle, const ui
     ZK_REQUIRE(pk.ek <= 24, "keygen: extended domain too large");
     ZK_REQUIRE(pk.bf + 1 < pk.n, "keygen: not enough rows");
     pk.omega = fr_omega(pk.k); pk.omega_inv = fr_omega_inv(pk.k);
-    pk.ext_omega = fr_omega(pk.ek); pk.ext_omega_inv = fr_omega_inv(pk.ek);
-    pk.n_inv = fr_pow2_inv(pk.k); pk.en_inv = fr_pow2_inv(pk.ek);
-    pk.zeta = fr_from_limbs(fr_consts::ZETA); pk.zeta_inv = fr_from_limbs(fr_consts::ZETA_INV);
+    pk.ext_omega = fr_omega(pk.ek);
+    pk.n_inv = fr_pow2_inv(pk.k);
+    pk.zeta = fr_from_limbs(fr_consts::ZETA);
     pk.plan.build(cs);
     cudaStream_t st = C.stream;
     const size_t n = pk.n, en = pk.cn;   // rows per coset-major column
