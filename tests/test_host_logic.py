@@ -159,3 +159,45 @@ def test_binary_inversion(hl, field, p):
     assert np.array_equal(euc, ref)
     want = [(pow(v, -1, p) * P.MONT_R % p) if v else 0 for v in vals]
     assert P.limbs_to_int(got.view(np.uint64)) == want
+
+
+def test_quotient_from_cosets_identity():
+    """The prover evaluates the quotient on Q cosets g_c * H of the size-n subgroup instead of halo2's 2^ek-point extended domain
+    (DESIGN.md "Quotient cosets").  Plain-integer check of the reconstruction k_coset_combine implements: for a random h of degree
+    < Q n, the size-n interpolants of its values on the cosets give back the pieces h_j through
+    h_j[m] = sum_c Vinv[j][c] * g_c^-m * hhat_c[m],  V[c][j] = (g_c^n)^j."""
+    import random
+    p = P.R_MOD
+    k, ek, Q = 3, 6, 5
+    n = 1 << k
+    rng = random.Random(3)
+    root = pow(7, (p - 1) >> 28, p)                     # ROOT_OF_UNITY
+    w_ext = pow(root, 1 << (28 - ek), p)
+    w = pow(w_ext, 1 << (ek - k), p)
+    zeta = 0x30644e72e131a029048b6e193fd84104cc37a73fec2bc5e9b8ca0b2d36636f23
+    assert pow(zeta, 3, p) == 1 and zeta != 1 and pow(w, n, p) == 1
+    h = [rng.randrange(p) for _ in range(Q * n)]
+    g = [zeta * pow(w_ext, c, p) % p for c in range(Q)]
+    ev = lambda x: sum(co * pow(x, i, p) for i, co in enumerate(h)) % p
+    n_inv = pow(n, -1, p)
+    hhat = []
+    for c in range(Q):
+        vals = [ev(g[c] * pow(w, t, p) % p) for t in range(n)]
+        hhat.append([n_inv * sum(vals[t] * pow(w, -t * m, p) for t in range(n)) % p for m in range(n)])   # inverse NTT of size n
+    # invert the Q x Q Vandermonde matrix in G_c = g_c^n (Gauss-Jordan mod p)
+    G = [pow(x, n, p) for x in g]
+    M = [[pow(G[c], j, p) for j in range(Q)] + [int(c == j) for j in range(Q)] for c in range(Q)]
+    for col in range(Q):
+        piv = next(r for r in range(col, Q) if M[r][col])
+        M[col], M[piv] = M[piv], M[col]
+        inv = pow(M[col][col], -1, p)
+        M[col] = [v * inv % p for v in M[col]]
+        for r in range(Q):
+            if r != col and M[r][col]:
+                f = M[r][col]
+                M[r] = [(a - f * b) % p for a, b in zip(M[r], M[col])]
+    vinv = [row[Q:] for row in M]
+    for j in range(Q):
+        for m in range(n):
+            got = sum(vinv[j][c] * pow(g[c], -m, p) * hhat[c][m] for c in range(Q)) % p
+            assert got == h[j * n + m]
