@@ -133,12 +133,14 @@ struct ProverWs {
     // host advice of the worker's NEXT sub-batch is uploaded on copy_stream into adv_next while the current one computes
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_ev = nullptr;
+    cudaEvent_t ev_pts = nullptr;    // "commitments of step 2 copied back" marker, reused by every sub-batch
     DevBuf<fr_t> adv_next;
     const fr_t* prefetched_src = nullptr;
     ~ProverWs() {
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (copy_ev) cudaEventDestroy(copy_ev);
+        if (ev_pts) cudaEventDestroy(ev_pts);
     }
     DevBuf<fr_t> adv, inst, z, randp, adv_ext, z_ext, h, hpoly, comb, hx, lx, tmp1, tmp2, scratch, evals, low;
     DevBuf<fr_t> lk_in, lk_tab, lk_a, lk_s, lk_z, lk_ext, sort_a, sort_t;   // lookups: [B][L][n] (lk_ext: [B][L][3][Qc*n])
@@ -179,6 +181,7 @@ struct PkEntry {
     std::vector<g1_affine_t> fixed_commitments, perm_commitments;
     QueryPlan plan;
     ProverWs ws[2];   // ws[0] also serves keygen; ws[1] is the second pipeline worker
+    mutable size_t cached_batch = 0;
 };
 
 static std::map<uint64_t, std::unique_ptr<PkEntry>> g_pks;
@@ -485,13 +488,17 @@ static LookupProgs lookup_progs(const PkEntry& pk) {
     return lp;
 }
 
+// Sub-batch size of a proving key.  Computed once per key (cudaMemGetInfo and the other allocator entry points take driver-wide
+// locks: on a box shared with other CUDA processes a call can stall for milliseconds, which is the single-proof latency budget).
 static size_t default_batch(const PkEntry& pk) {
     if (const char* e = getenv("ZKGPU_PROVER_BATCH")) { long v = atol(e); if (v > 0) return (size_t)v; }
+    if (pk.cached_batch) return pk.cached_batch;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     size_t per = ((size_t)(pk.A + 1 + pk.P + 1 + 3 * pk.L) * pk.cn + (size_t)(pk.A + 2 * pk.P + 7 * pk.L + 8 + 3 * pk.plan.sets.size()) * pk.n) * sizeof(fr_t);
     size_t B = (size_t)(free_b * 0.2) / std::max<size_t>(per, 1);
-    return std::max<size_t>(1, std::min<size_t>(B, 128));
+    pk.cached_batch = std::max<size_t>(1, std::min<size_t>(B, 128));
+    return pk.cached_batch;
 }
 
 static void ensure_ws(PkEntry& pk, ProverWs& W, size_t B) {
@@ -676,8 +683,8 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
     trace_dev("random_poly", W.randp.p, n, 1, n, st);
     commit(C, pk, W, 0, W.randp.p, B, 0, 0, W.aff.p + B * (P + L), st);
     ZK_CUDA(cudaMemcpyAsync(W.h_aff.p, W.aff.p, B * (P + L + 1) * sizeof(g1_affine_t), cudaMemcpyDeviceToHost, st));
-    cudaEvent_t ev_pts;
-    ZK_CUDA(cudaEventCreateWithFlags(&ev_pts, cudaEventDisableTiming));
+    if (!W.ev_pts) ZK_CUDA(cudaEventCreateWithFlags(&W.ev_pts, cudaEventDisableTiming));
+    cudaEvent_t ev_pts = W.ev_pts;
     ZK_CUDA(cudaEventRecord(ev_pts, st));
     // queue the transforms that do not depend on y behind the commitments
     if (P) {
@@ -695,7 +702,6 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
     coset_ext(pk, W, W.adv.p, W.adv_ext.p, B, A, (A + 1) * en, st);
     coset_ext(pk, W, W.inst.p, W.adv_ext.p + A * en, B, 1, (A + 1) * en, st);
     ZK_CUDA(cudaEventSynchronize(ev_pts));
-    ZK_CUDA(cudaEventDestroy(ev_pts));
     {
         const g1_affine_t* pts = W.h_aff.as<g1_affine_t>();
         for (size_t b = 0; b < B; ++b) {
