@@ -505,7 +505,8 @@ static void ensure_ws(PkEntry& pk, ProverWs& W, size_t B) {
     const size_t n = pk.n, en = pk.cn, ns = pk.plan.sets.size();
     W.B = std::max(W.B, B);
     W.adv.ensure(B * pk.A * n); W.inst.ensure(B * n); W.z.ensure(std::max<size_t>(1, B * pk.P * n)); W.randp.ensure(B * n);
-    W.adv_ext.ensure(B * (pk.A + 1) * en); W.z_ext.ensure(std::max<size_t>(1, B * pk.P * en)); W.h.ensure(B * en);
+    // adv_ext doubles as scratch for the grand-product numerators / denominators (2 x [B][P + L][n]) before it is filled
+    W.adv_ext.ensure(std::max(B * (pk.A + 1) * en, 2 * B * (pk.P + pk.L) * n)); W.z_ext.ensure(std::max<size_t>(1, B * pk.P * en)); W.h.ensure(B * en);
     W.hpoly.ensure(B * n); W.comb.ensure(B * ns * n); W.hx.ensure(B * n); W.lx.ensure(B * n);
     W.tmp1.ensure(B * ns * n); W.tmp2.ensure(B * ns * n);
     W.evals.ensure(B * (pk.num_evals + 1)); W.low.ensure(B * (ns + 1) * 4);
@@ -522,7 +523,6 @@ static void ensure_ws(PkEntry& pk, ProverWs& W, size_t B) {
     size_t max_pts = B * std::max<size_t>(std::max<size_t>(pk.A, pk.P + pk.L + 1), std::max<size_t>(pk.Q, 2 * pk.L + 1));
     W.aff.ensure(max_pts);
     W.h_aff.ensure(max_pts * sizeof(g1_affine_t)); W.h_evals.ensure(B * (pk.num_evals + 1) * sizeof(fr_t));
-    ZK_REQUIRE(2 * B * (pk.P + pk.L) * n <= B * (pk.A + 1) * en, "workspace aliasing assumption violated");
 }
 
 static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* advice, bool advice_on_device, const fr_t* instance, size_t num_pi,
