@@ -15,15 +15,17 @@ ROOT = O.ROOT
 CSRC = os.path.join(ROOT, "zkos-monorepo_b200", "csrc")
 
 
-@pytest.fixture(scope="module", params=["schoolbook", "karatsuba"])
+@pytest.fixture(scope="module", params=["schoolbook", "karatsuba", "plain_sqr"])
 def emu(request, tmp_path_factory):
-    """schoolbook = the shipped interleaved product (regenerated in place and required to be unchanged);
+    """schoolbook = the shipped interleaved product with the triangular squaring (regenerated in place and required to be unchanged);
     karatsuba = the optional ZK_FP_KARATSUBA=1 variant, generated into a scratch directory."""
     d = tmp_path_factory.mktemp("emu_" + request.param)
     if request.param == "schoolbook":
         shipped = open(os.path.join(CSRC, "fp_gen.inc")).read()
         subprocess.check_call(["python3", os.path.join(CSRC, "gen_fp.py"), str(d / "fp_gen.inc")], env=dict(os.environ, ZK_FP_KARATSUBA="0"))
         assert open(str(d / "fp_gen.inc")).read() == shipped, "csrc/fp_gen.inc is stale: run gen_fp.py"
+    elif request.param == "plain_sqr":   # squaring emitted as mul(a, a) instead of the triangular product
+        subprocess.check_call(["python3", os.path.join(CSRC, "gen_fp.py"), str(d / "fp_gen.inc")], env=dict(os.environ, ZK_FP_KARATSUBA="0", ZK_FP_TRISQR="0"))
     else:
         subprocess.check_call(["python3", os.path.join(CSRC, "gen_fp.py"), str(d / "fp_gen.inc")], env=dict(os.environ, ZK_FP_KARATSUBA="1"))
     so = str(d / "libfpemu.so")
@@ -45,7 +47,9 @@ def run(emu, field, op, a, b=None):
 def test_limb_arithmetic_matches_oracle(emu, field, p):
     rng = np.random.default_rng(7 + field)
     edge = [0, 1, 2, p - 1, p - 2, (1 << 253) - 1, (1 << 253), (1 << 32) - 1, (1 << 64) - 1, 0xFFFFFFFF << 224 | 5,
-            (1 << 128) - 1, 1 << 128, ((1 << 125) << 128) | (1 << 125), ((1 << 128) - 1) << 120, (3 << 128) | 7, (7 << 128) | 3]
+            (1 << 128) - 1, 1 << 128, ((1 << 125) << 128) | (1 << 125), ((1 << 128) - 1) << 120, (3 << 128) | 7, (7 << 128) | 3,
+            # bit 31 of a limb is the bit the triangular squaring moves between the doubled limbs
+            0x7fffffff, 0x80000000, 0x80000000 << 32, (0x80000000 << 192) | 0x80000000, int("80000000" * 7, 16), int("ffffffff" * 7, 16)]
     edge = [e % p for e in edge]
     vals_a = edge * len(edge) + [int.from_bytes(rng.bytes(40), "little") % p for _ in range(20000)]
     vals_b = [e for e in edge for _ in edge] + [int.from_bytes(rng.bytes(40), "little") % p for _ in range(20000)]

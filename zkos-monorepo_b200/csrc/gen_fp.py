@@ -120,8 +120,14 @@ def emit_c_chain(chain, check_carry_free):
     return "\n".join(out)
 
 
-def gen_mont_mul(mod, sqr=False):
-    """Returns list of (chain, carry_must_be_zero) computing r = a*b/2^256 mod p into r[0..7]."""
+def gen_mont_mul(mod, sqr=False, tri=False):
+    """Returns list of (chain, carry_must_be_zero) computing r = a*b/2^256 mod p into r[0..7].
+
+    tri (squaring only): triangular product.  a^2 = sum_i a_i 2^(32 i) * (a_i 2^(32 i) + sum_{j>i} 2 a_j 2^(32 j)), so step i
+    multiplies a_i by the limbs j >= i of (a_i, 2a) only: 36 wide products instead of 64.  d = 2a is one carry chain of eight
+    adds; the limbs j > i of 2a are d[j] except that bit 0 of d[i+1] (= bit 31 of a_i) belongs to 2 a_i: dm[j] = d[j] & ~1.
+    Skipped products become plain carry-propagating adds (ALU pipe), which still perform the frame shift of the interleaved
+    reduction."""
     M = limbs32(mod)
     m0 = (-pow(mod, -1, 1 << 32)) % (1 << 32)
     p = Prog()
@@ -130,31 +136,62 @@ def gen_mont_mul(mod, sqr=False):
     Bv = ["b[%d]" % i for i in range(N)] if not sqr else A
     ev = ["ev[%d]" % i for i in range(N)]
     od = ["od[%d]" % i for i in range(N)]
+    tri = tri and sqr
+    if tri:
+        p.chain(); flags.append(False)
+        p.ins("add.cc", "d[0]", A[0], A[0])
+        for i in range(1, N - 1):
+            p.ins("addc.cc", "d[%d]" % i, A[i], A[i])
+        p.ins("addc", "d[%d]" % (N - 1), A[N - 1], A[N - 1])
+        p.chain(); flags.append(False)
+        for i in range(1, N):
+            p.ins("and", "dm[%d]" % i, "d[%d]" % i, 0xFFFFFFFE)
 
-    def step(e, o, bi, first):
+    def mad(op, dst, x, bi, addend=None):
+        if x is not None:
+            if addend is None:
+                p.ins(op, dst, x, bi)
+            else:
+                p.ins(op, dst, x, bi, addend)
+            return
+        name, cc = op.split(".")[0], op.endswith(".cc")
+        assert name in ("mad", "madc") and addend is not None
+        p.ins(("add" if name == "mad" else "addc") + (".cc" if cc else ""), dst, addend, 0)
+
+    def step(e, o, bi, first, i):
+        def X(j):
+            if not tri:
+                return A[j]
+            if j < i:
+                return None
+            return A[j] if j == i else ("dm[%d]" % j if j == i + 1 else "d[%d]" % j)
         if first:
             p.chain(); flags.append(False)
             for j in range(0, N, 2):
-                p.ins("mul.lo", o[j], A[j + 1], bi)
-                p.ins("mul.hi", o[j + 1], A[j + 1], bi)
+                p.ins("mul.lo", o[j], X(j + 1), bi)
+                p.ins("mul.hi", o[j + 1], X(j + 1), bi)
             for j in range(0, N, 2):
-                p.ins("mul.lo", e[j], A[j], bi)
-                p.ins("mul.hi", e[j + 1], A[j], bi)
+                p.ins("mul.lo", e[j], X(j), bi)
+                p.ins("mul.hi", e[j + 1], X(j), bi)
         else:
             p.chain(); flags.append(False)
             p.ins("add.cc", e[0], e[0], o[1])
             for j in range(0, N - 2, 2):
-                p.ins("madc.lo.cc", o[j], A[j + 1], bi, o[j + 2])
-                p.ins("madc.hi.cc", o[j + 1], A[j + 1], bi, o[j + 3])
-            p.ins("madc.lo.cc", o[N - 2], A[N - 1], bi, 0)
-            p.ins("madc.hi", o[N - 1], A[N - 1], bi, 0)
+                mad("madc.lo.cc", o[j], X(j + 1), bi, o[j + 2])
+                mad("madc.hi.cc", o[j + 1], X(j + 1), bi, o[j + 3])
+            mad("madc.lo.cc", o[N - 2], X(N - 1), bi, 0)
+            mad("madc.hi", o[N - 1], X(N - 1), bi, 0)
             p.chain(); flags.append(False)
-            p.ins("mad.lo.cc", e[0], A[0], bi, e[0])
-            p.ins("madc.hi.cc", e[1], A[0], bi, e[1])
-            for j in range(2, N, 2):
-                p.ins("madc.lo.cc", e[j], A[j], bi, e[j])
-                p.ins("madc.hi.cc", e[j + 1], A[j], bi, e[j + 1])
-            p.ins("addc", o[N - 1], o[N - 1], 0)
+            j0 = 0
+            while tri and j0 < N and X(j0) is None:      # leading skipped products of a chain without carry-in: nothing to do
+                j0 += 2
+            if j0 < N:
+                p.ins("mad.lo.cc", e[j0], X(j0), bi, e[j0])
+                p.ins("madc.hi.cc", e[j0 + 1], X(j0), bi, e[j0 + 1])
+                for j in range(j0 + 2, N, 2):
+                    mad("madc.lo.cc", e[j], X(j), bi, e[j])
+                    mad("madc.hi.cc", e[j + 1], X(j), bi, e[j + 1])
+                p.ins("addc", o[N - 1], o[N - 1], 0)
         p.chain(); flags.append(False)
         p.ins("mul.lo", "mi", e[0], m0)
         # odd += MOD[odd limbs] * mi   (top carry is provably zero; the emulation asserts it)
@@ -173,8 +210,8 @@ def gen_mont_mul(mod, sqr=False):
         p.ins("addc", o[N - 1], o[N - 1], 0)
 
     for i in range(0, N, 2):
-        step(ev, od, Bv[i], i == 0)
-        step(od, ev, Bv[i + 1], False)
+        step(ev, od, Bv[i], i == 0, i)
+        step(od, ev, Bv[i + 1], False, i + 1)
     # merge: ev[i] += od[i+1]
     p.chain(); flags.append(False)
     p.ins("add.cc", ev[0], ev[0], od[1])
@@ -369,6 +406,9 @@ def gen_mont_mul_karatsuba(mod, sqr=False):
 # interleaved schoolbook product — ptxas leaves some lo/hi pairs unfused and moves carry adds onto the IMAD pipe
 # (IMAD.X / IMAD.MOV), which eats the 16 saved wide multiplies.  Kept as an option (ZK_FP_KARATSUBA=1), off by default.
 KARATSUBA = os.environ.get("ZK_FP_KARATSUBA", "0") != "0"
+# Triangular squaring (36 instead of 64 wide products in the a*a part; see gen_mont_mul): 92 instead of 120 IMAD.WIDE per squaring in SASS,
+# bucket accumulation (8M + 2S per mixed addition) 1008 -> 987 ms per 1024 proofs on B200.  ZK_FP_TRISQR=0 emits sqr as mul(a, a).
+TRISQR = os.environ.get("ZK_FP_TRISQR", "1") != "0"
 
 
 def gen_add(mod):
@@ -425,12 +465,15 @@ def emit_field(name, mod):
     for cname, vals in (("one", R), ("r2", R2), ("modm2", limbs32(mod - 2))):
         o.append("ZK_FP_FN void %s_set_%s(uint32_t* r) { %s }" % (name, cname, " ".join("r[%d] = 0x%08xu;" % (i, v) for i, v in enumerate(vals))))
     mulgen = gen_mont_mul_karatsuba if KARATSUBA else gen_mont_mul
-    for fn, gen in (("mul", lambda: mulgen(mod)), ("sqr", lambda: mulgen(mod, sqr=True))):
+    sqrgen = (lambda: gen_mont_mul(mod, sqr=True, tri=True)) if (TRISQR and not KARATSUBA) else (lambda: mulgen(mod, sqr=True))
+    for fn, gen in (("mul", lambda: mulgen(mod)), ("sqr", sqrgen)):
         sig = "ZK_FP_FN void %s_%s(uint32_t* __restrict__ r, const uint32_t* __restrict__ a%s)" % (
             name, fn, ", const uint32_t* __restrict__ b" if fn == "mul" else "")
         chains = gen()
         o.append(sig + " {")
         o.append("    uint32_t ev[8] = {0,0,0,0,0,0,0,0}, od[8] = {0,0,0,0,0,0,0,0}, t[8] = {0,0,0,0,0,0,0,0}, mi = 0, bw = 0;")
+        if fn == "sqr" and TRISQR and not KARATSUBA:
+            o.append("    uint32_t d[8] = {0,0,0,0,0,0,0,0}, dm[8] = {0,0,0,0,0,0,0,0};")
         if KARATSUBA:
             o.append("    uint32_t z0[8] = {0}, z2[8] = {0}, zm[8] = {0}, pe0[8] = {0}, po0[8] = {0}, pe1[8] = {0}, po1[8] = {0}, pe2[8] = {0}, po2[8] = {0};")
             o.append("    uint32_t da[4] = {0}, db[4] = {0}, mid[9] = {0}, tt[16] = {0}, sa = 0, sb = 0, sn = 0, cz = 0; (void)cz;")
