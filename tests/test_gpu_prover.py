@@ -301,6 +301,23 @@ def test_two_pipeline_workers_and_ragged_sub_batches(tiny, monkeypatch):
     assert out.tobytes() == b"".join(proofs)
 
 
+def test_config0_deposit_proof_equals_the_cpu_anchor():
+    """BASELINE configs[0] on the GPU: the seeded k = 13 deposit-shaped proof has the SHA-256 that tests/test_oracle_plonk.py pins
+    for the CPU prover restatement (a regression anchor of this repository's prover pair, not a reference vector)."""
+    zkgpu.init(0)
+    shape = circuits.Shape("deposit")
+    circ = circuits.Circuit(shape, O.OracleBackend, seed=3)
+    srs = O.params_setup(shape.k, 42, threads=8)
+    params = zkgpu.ParamsKZG(shape.k, srs["g"], srs["g_lagrange"])
+    pk = zkgpu.ProvingKey(params, circ.blob)
+    try:
+        adv, pi = circ.witness(1)
+        proof = pk.prove(adv, pi, 42)
+        assert hashlib.sha256(proof).hexdigest() == "58b777cfa2f6db0171d2c05bd7ad8ff726e245fd07d33af773174ad00d914abd"
+    finally:
+        pk.release(); params.release()
+
+
 def test_rayon_thread_count_chunks_the_random_polynomial(tiny):
     """halo2's vanishing prover seeds one ChaCha20 stream per chunk of n / rayon::current_num_threads() coefficients, so the proof
     bytes depend on the host's thread count: with the same setting on both sides the GPU proofs equal the CPU prover's

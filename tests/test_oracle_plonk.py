@@ -147,3 +147,23 @@ def test_rayon_thread_count_changes_only_the_random_polynomial(setup):
     finally:
         O.set_rayon_threads(1)
     assert po.prove(adv, pi, seed=9) == base
+
+
+def test_config0_single_deposit_proof_on_cpu_seeded():
+    """BASELINE configs[0]: one deposit-shaped proof through the CPU prover restatement at k = 13 with the seeded SRS
+    (`ParamsKZG::setup`, seed 42: ppot_0080_13 is not in the reference tree) and `SmallRng::seed_from_u64(42)`
+    (/root/reference/crates/shielder-setup/lib.rs:19,29-40).  The proof verifies, is deterministic, and its SHA-256 is pinned as a
+    REGRESSION anchor of this repository's own prover pair (CPU restatement and, in test_gpu_prover / bench.py, the byte-identical
+    GPU prover) — it is not a vector of the reference, which holds no golden proofs."""
+    import hashlib
+    shape = circuits.Shape("deposit")
+    circ = circuits.Circuit(shape, O.OracleBackend, seed=3)
+    srs = O.params_setup(shape.k, 42, threads=8)
+    po = O.PlonkOracle(circ.blob, srs, threads=8)
+    adv, pi = circ.witness(1)
+    proof = po.prove(adv, pi, seed=42)
+    assert len(proof) == shape.proof_len == 4544
+    assert po.verify(proof, pi)
+    assert hashlib.sha256(proof).hexdigest() == "58b777cfa2f6db0171d2c05bd7ad8ff726e245fd07d33af773174ad00d914abd"
+    wrong = pi.copy(); wrong[0, 0] ^= 1
+    assert not po.verify(proof, wrong)
