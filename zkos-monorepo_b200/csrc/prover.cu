@@ -997,15 +997,23 @@ static void prove_batch(uint64_t handle, const uint64_t* advice, bool advice_on_
     if (workers == 2 && Bmax > 1) { Bmax = std::max<size_t>(1, std::min(Bmax, (m + 3) / 4)); nsub = (m + Bmax - 1) / Bmax; }
     const fr_t* adv = reinterpret_cast<const fr_t*>(advice);
     const fr_t* inst = reinterpret_cast<const fr_t*>(instance);
+    // sub-batches as (offset, count).  With host advice the very first one is a quarter of the usual size: nothing can hide its
+    // upload, so the GPU should start on a short one while the other worker's full-size upload is still in flight.
+    std::vector<std::pair<size_t, size_t>> segs;
+    {
+        size_t off = 0;
+        if (workers == 2 && !advice_on_device && m > Bmax && Bmax >= 8) { segs.push_back({0, Bmax / 4}); off = Bmax / 4; }
+        while (off < m) { size_t B = std::min(Bmax, m - off); segs.push_back({off, B}); off += B; }
+    }
     auto run = [&](unsigned w) {
         ZK_CUDA(cudaSetDevice(C.device));
         pk.ws[w].prefetched_src = nullptr;
-        for (size_t sb = w; sb < nsub; sb += workers) {
-            size_t off = sb * Bmax, B = std::min(Bmax, m - off);
-            size_t nsb = sb + workers, noff = nsb * Bmax;
-            const fr_t* next = nsb < nsub ? adv + noff * pk.A * pk.n : nullptr;
+        for (size_t i = w; i < segs.size(); i += workers) {
+            const size_t off = segs[i].first, B = segs[i].second;
+            const bool has_next = i + workers < segs.size();
+            const fr_t* next = has_next ? adv + segs[i + workers].first * pk.A * pk.n : nullptr;
             prove_sub_batch(C, pk, pk.ws[w], adv + off * pk.A * pk.n, advice_on_device, inst + off * num_pi, num_pi, B, seeds + off,
-                            proofs + off * proof_len, next, next ? std::min(Bmax, m - noff) : 0);
+                            proofs + off * proof_len, next, has_next ? segs[i + workers].second : 0);
         }
     };
     if (workers == 1) { run(0); return; }
