@@ -399,7 +399,7 @@ static std::unique_ptr<PkEntry> keygen(Context& C, uint64_t srs_handle, const ui
         for (unsigned c = 0; c < pk.S; ++c) { cols[c].type = cs.perm_columns[c].type; cols[c].index = cs.perm_columns[c].index; }
         upload(pk.cols, cols, st);
     }
-    // l_0, l_blind, l_last on the extended coset; l_active_row = 1 - l_last - l_blind
+    // l_0, l_blind, l_last on the quotient cosets; l_active_row = 1 - l_last - l_blind
     {
         std::vector<fr_t> lag(3 * n, fr_t::zero());
         fr_t one = fe_one<FrTag>();

@@ -255,7 +255,7 @@ void launch_chacha_poly(const uint8_t* seeds, fr_t* out, size_t n, size_t B, siz
 }
 
 // ---------------------------------------------------------------------------------------------
-// evaluate_h: quotient numerator on the extended coset, divided by the vanishing polynomial
+// evaluate_h: quotient numerator on the Qc quotient cosets (coset-major rows), divided by the vanishing polynomial
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_eval_h(const EvalHArgs a, fr_t* h, size_t B) {
     // Rows are coset-major: row i = c * n + r is the point g_c * omega^r, g_c = zeta * ext_omega^c, c < Qc.  `en` below is

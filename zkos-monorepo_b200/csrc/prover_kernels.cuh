@@ -67,7 +67,7 @@ void launch_lookup_num_den(const fr_t* comp_in, const fr_t* comp_tab, const fr_t
                            fr_t* num, fr_t* den, unsigned k, unsigned L, size_t B, cudaStream_t st);
 
 struct EvalHArgs {
-    // per-proof extended cosets
+    // per-proof columns on the quotient cosets
     const fr_t* adv_ext; size_t adv_ext_proof_stride;  // [B][A+1][Qc*n], instance coset at column A
     const fr_t* z_ext;   size_t z_ext_proof_stride;    // [B][P][Qc*n]
     // proving key
@@ -86,7 +86,7 @@ struct EvalHArgs {
     const int32_t* adv_q;  // [num_advice_queries][2] = (column, rotation)
     const int32_t* fix_q;
     const int32_t* inst_q;
-    // lookups: extended cosets [B][L][3][Qc*n] in the order (z, permuted input, permuted table)
+    // lookups: quotient cosets [B][L][3][Qc*n] in the order (z, permuted input, permuted table)
     const fr_t* lk_ext; size_t lk_ext_proof_stride;
     LookupProgs lp;
     unsigned num_gates, A, S, chunk, P, k, ek;
