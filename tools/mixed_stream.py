@@ -74,9 +74,9 @@ def main():
             adv[j] = wits[t][i % args.distinct][0]
         inst = np.stack([wits[t][i % args.distinct][1] for i in idx])
         batches[t] = (adv, inst, np.array(idx, dtype=np.uint64) + 1)
-    for t in TYPES:                                            # warm-up: two full sub-batches per circuit, so that both pipeline
-        if by_type[t]:                                         # workers' workspaces exist before the timed region
-            w = min(len(by_type[t]), 4 * pks[t].sub_batch)   # 4: every worker also runs one background advice prefetch
+    for t in TYPES:                                            # warm-up: enough sub-batches per circuit that every pipeline
+        if by_type[t]:                                         # worker's workspace and prefetch buffer exist before the timed region
+            w = min(len(by_type[t]), 7 * pks[t].sub_batch)   # 7: all three workers run, each with a background advice prefetch
             pks[t].prove_batch(batches[t][0][:w], batches[t][1][:w], batches[t][2][:w])
     if dist is not None:
         dist.barrier()
