@@ -21,9 +21,12 @@
  *   - G1 projective results: Jacobian (X, Y, Z) as 12 x u64, returned normalised (Z = 1, or
  *     (0,1,0) for the identity) — projective representatives are not canonical, the group element is.
  *   - All pointers are host memory unless the function name ends in `_dev`.
- *   - All functions are synchronous, thread-safe, return 0 on success and a negative code otherwise;
- *     zkgpu_last_error() gives the thread-local message.  The upstream functions are infallible and
- *     panic on misuse; the Rust shim maps a non-zero return to `panic!`.
+ *   - All functions are synchronous, thread-safe and re-entrant, return 0 on success and a negative code
+ *     otherwise; zkgpu_last_error() gives the thread-local message.  The upstream functions are infallible
+ *     and panic on misuse; the Rust shim maps a non-zero return to `panic!`.
+ *   - There is no process-wide lock.  The primitive calls (MSM / NTT / G1-FFT) serialise per device on the
+ *     scratch buffers they share; proving calls serialise per proving key and device; zkgpu_prove callers
+ *     never serialise: concurrent requests are coalesced into lock-step batches.
  *   - There is no CPU fallback: without a CUDA device every compute call fails with ZKGPU_ERR_CUDA.
  */
 #ifndef ZKGPU_H
@@ -40,10 +43,17 @@ extern "C" {
 #define ZKGPU_ERR_ARG (-2)
 #define ZKGPU_ERR_STATE (-3)
 #define ZKGPU_ERR_INTERNAL (-4)
+#define ZKGPU_ERR_WITNESS (-5)   /* create_proof failed for THIS witness (plonk::Error::ConstraintSystemFailure) */
 
-/* Binds the calling process to the CUDA device `device` (one process per GPU). Idempotent. */
-int zkgpu_init(int device);
+/* Selects the CUDA devices this process proves on: bit i of `device_mask` = CUDA device i,
+ * 0 = every visible device.  Idempotent for the same mask; once per process, thread-safe.  Without a call the first
+ * compute entry point selects device 0.  Key material (SRS tables, proving keys) is replicated on every selected
+ * device; the primitive calls run on the lowest selected device, zkgpu_prove_batch / zkgpu_prove on all of them. */
+int zkgpu_init(int device_mask);
 void zkgpu_shutdown(void);
+/* number of selected devices / CUDA index of the i-th one (-1 if out of range) */
+int zkgpu_device_count(void);
+int zkgpu_device_index(int slot);
 const char* zkgpu_last_error(void);
 /* ABI version of this header (bumped on any signature change). */
 int zkgpu_abi_version(void);
@@ -83,6 +93,9 @@ int zkgpu_g_to_lagrange(const uint64_t* g_affine, uint32_t k, uint64_t* out_affi
 /* ParamsKZG::setup(k, SmallRng::seed_from_u64(seed)) — the seeded SRS of the reference's prove/verify tests
  * (/root/reference/crates/halo2-verifier/src/generator.rs:118-119): g[i] = G * s^i, g_lagrange = g_to_lagrange(g). */
 int zkgpu_params_setup(uint32_t k, uint64_t seed, uint64_t* g_out, uint64_t* g_lagrange_out);
+/* The same from a RUNNING SmallRng: rng_state is the caller's xoshiro256++ state (rand 0.8.5 SmallRng on 64-bit targets), advanced
+ * by the one `Fr::random` that setup draws — generator.rs:117-120 hands one rng to setup, witness generation and the prover in turn. */
+int zkgpu_params_setup_rng(uint32_t k, uint64_t rng_state[4], uint64_t* g_out, uint64_t* g_lagrange_out);
 
 /* g_lagrange_out may be NULL (then k up to 24: bases for the large-MSM sweep). */
 
@@ -100,6 +113,8 @@ int zkgpu_fr_vec_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out,
 int zkgpu_fr_to_mont(const uint64_t* canonical, uint64_t* out, size_t n);
 int zkgpu_fr_from_mont(const uint64_t* mont, uint64_t* out, size_t n);
 int zkgpu_fr_random(uint64_t seed, uint64_t* out, size_t n);
+/* n x `Fr::random(&mut rng)` from a running SmallRng (state advanced in place) */
+int zkgpu_fr_random_rng(uint64_t rng_state[4], uint64_t* out, size_t n);
 
 /* ---- Poseidon2 (t = 8, rate 7) and the note-tree Merkle path: witness-side hashing --------------------------------
  * shielder_bindings::hash::poseidon_hash = hash_variable_length (/root/reference/crates/shielder_bindings/src/hash.rs:16-27,
@@ -134,23 +149,62 @@ int zkgpu_msm_g1_srs_batch_dev(uint64_t srs, int basis, const void* d_scalars, s
  * The SRS handle must have been registered with the same k (ParamsKZG::downsize first). */
 int zkgpu_pk_create(uint64_t srs, const uint8_t* circuit_blob, size_t blob_len, uint64_t* pk_out);
 int zkgpu_pk_release(uint64_t pk);
-/* info[0..13] = k, n, num_advice, num_fixed, degree, blinding_factors, num_perm_sets, num_quotients,
- *               num_evals, proof_len, extended_k, num_perm_columns, num_rotation_sets, sub_batch */
+/* info[0..14] = k, n, num_advice, num_fixed, degree, blinding_factors, num_perm_sets, num_quotients,
+ *               num_evals, proof_len, extended_k, num_perm_columns, num_rotation_sets, sub_batch, replicas (devices) */
 int zkgpu_pk_info(uint64_t pk, uint64_t info[16]);
 /* VerifyingKey parts: fixed commitments (F x 8 u64 affine), permutation commitments (S x 8), transcript_repr (4) */
 int zkgpu_pk_vk(uint64_t pk, uint64_t* fixed_commitments, uint64_t* perm_commitments, uint64_t digest[4]);
+/* ---- the proof's randomness: `rng: &mut impl RngCore` of generate_proof --------------------------------------------
+ * The reference passes a RUNNING `SmallRng` in its seeded tests — the same rng has already produced the SRS and the witness
+ * (/root/reference/crates/halo2-verifier/src/generator.rs:117-130) — and `OsRng` / `thread_rng()` in production
+ * (/root/reference/crates/shielder-account/src/call_data.rs:499, /root/reference/crates/shielder_bindings/src/circuits/deposit.rs:108).
+ * rng_mode selects what `rng_data` holds for each proof:
+ *   ZKGPU_RNG_SEED_U64      m x u64        SmallRng::seed_from_u64(seed): TEST / PARITY ONLY — 64 bits of entropy and a
+ *                                          non-cryptographic generator do not hide a witness.
+ *   ZKGPU_RNG_XOSHIRO_STATE m x 4 x u64    a running SmallRng (xoshiro256++ state), IN/OUT: the state after the proof's last
+ *                                          draw is written back, so the host's rng continues exactly as `&mut rng` does
+ *                                          upstream.  Reproduces the reference's seeded prove-and-verify tests.  Not a CSPRNG.
+ *   ZKGPU_RNG_CHACHA20_SEED m x 32 bytes   ChaCha20Rng::from_seed(seed) (rand_chacha 0.3.1): PRODUCTION — the caller draws 32
+ *                                          bytes per proof from `OsRng` / `thread_rng()`; every blinding value of the proof comes
+ *                                          from that 256-bit-keyed ChaCha20 stream. */
+#define ZKGPU_RNG_SEED_U64 0
+#define ZKGPU_RNG_XOSHIRO_STATE 1
+#define ZKGPU_RNG_CHACHA20_SEED 2
+/* per-proof status */
+#define ZKGPU_PROOF_OK 0
+#define ZKGPU_PROOF_LOOKUP_FAILED 1   /* a lookup input is not in its table: plonk::Error::ConstraintSystemFailure for that proof */
+
 /* m proofs.  advice: m x num_advice x n field elements — the assigned advice columns `create_proof` holds
  * after witness synthesis (rows >= n - (blinding_factors + 1) are overwritten with blinding values);
- * instance: m x num_instance public inputs; rng_seeds[i] seeds proof i's `SmallRng::seed_from_u64`
- * (/root/reference/crates/shielder-setup/lib.rs:29-40); proofs_out: m x proof_len bytes, each exactly what
- * `transcript.finalize()` returns (/root/reference/crates/halo2-verifier/src/lib/verifier_contract.rs:14-20). */
+ * instance: m x num_instance public inputs; proofs_out: m x proof_len bytes, each exactly what
+ * `transcript.finalize()` returns (/root/reference/crates/halo2-verifier/src/lib/verifier_contract.rs:14-20).
+ * With several selected devices the batch is split into contiguous shards, one per device.
+ * A witness that makes create_proof fail fails ALONE, as one request of the reference's prover server does
+ * (/root/reference/tee/crates/shielder-prover-tee/src/server.rs:189-190): status_out[i] (may be NULL) receives its
+ * ZKGPU_PROOF_* code, its proof bytes are zeroed, and the other m - 1 proofs are complete and valid; the call returns 0. */
+int zkgpu_prove_batch_rng(uint64_t pk, const uint64_t* advice, const uint64_t* instance, size_t num_instance, size_t m,
+                          int rng_mode, void* rng_data, uint8_t* proofs_out, size_t proof_len, int32_t* status_out);
+/* same with the advice columns already resident in HBM of one selected device (that device proves the whole batch) */
+int zkgpu_prove_batch_rng_dev(uint64_t pk, const void* d_advice, const uint64_t* instance, size_t num_instance, size_t m,
+                              int rng_mode, void* rng_data, uint8_t* proofs_out, size_t proof_len, int32_t* status_out);
+/* Test / parity form of the above: rng_mode = ZKGPU_RNG_SEED_U64 (rng_seeds[i] seeds proof i,
+ * /root/reference/crates/shielder-setup/lib.rs:29-40) and all-or-nothing: ZKGPU_ERR_ARG if any proof failed. */
 int zkgpu_prove_batch(uint64_t pk, const uint64_t* advice, const uint64_t* instance, size_t num_instance, size_t m,
                       const uint64_t* rng_seeds, uint8_t* proofs_out, size_t proof_len);
+/* ONE proof, blocking: the call a per-request host makes where the reference calls generate_proof — one tokio task per
+ * client, up to 100 in flight (/root/reference/tee/crates/shielder-prover-tee/src/server.rs:157-195,
+ * /root/reference/tee/crates/shielder-prover-server/src/command_line_args.rs:24-27).  Callable from any number of threads:
+ * requests waiting at the same time are coalesced into lock-step batches across every selected device; no caller waits on a
+ * lock around the GPU.  rng_data as above for ONE proof.  A failing witness returns ZKGPU_ERR_WITNESS to its caller only. */
+int zkgpu_prove(uint64_t pk, const uint64_t* advice, const uint64_t* instance, size_t num_instance, int rng_mode, void* rng_data,
+                uint8_t* proof_out, size_t proof_len);
+/* coalescer statistics of a proving key: out = {requests served, batches run, largest batch, dispatcher threads} */
+int zkgpu_prove_stats(uint64_t pk, uint64_t out[4]);
 /* halo2's vanishing prover draws the random polynomial in chunks of n / rayon::current_num_threads() coefficients, each from its
  * own ChaCha20 stream seeded from the proof's rng, so proof bytes depend on the host's rayon thread count.  Tell the
  * library the thread count of the host it replaces (default 1 = a single stream, the `multicore` feature off / RAYON_NUM_THREADS=1). */
 int zkgpu_set_rayon_threads(unsigned num_threads);
-/* same with the advice columns already resident in HBM */
+/* zkgpu_prove_batch with the advice columns already resident in HBM */
 int zkgpu_prove_batch_dev(uint64_t pk, const void* d_advice, const uint64_t* instance, size_t num_instance, size_t m,
                           const uint64_t* rng_seeds, uint8_t* proofs_out, size_t proof_len);
 /* profiling aid: accumulated wall-clock seconds per prover step (0 upload, 1 advice commit, 2 permutation +
@@ -162,10 +216,11 @@ void zkgpu_set_trace(void (*fn)(const char* name, const void* data, size_t bytes
 /* Per-kernel-class device timing (bench.py's roofline line): when enabled, CUDA events are recorded on the
  * launching stream around every launch group of a class.  Slots: 0 MSM bucket accumulation, 1 MSM digit
  * sort (count/scan/scatter), 2 MSM bucket reduction, 3 NTT tile passes, 4 quotient evaluation,
- * 5 permutation products, 6 polynomial evaluation / SHPLONK algebra. */
+ * 5 permutation / lookup grand products, 6 polynomial evaluation / SHPLONK algebra, 7 lookup compression +
+ * permuted columns, 8 the rest (blinding scatter, ChaCha20 polynomial, affine normalisation). */
 void zkgpu_kernel_timing(int enable);
 int zkgpu_kernel_times(int slot, double* total_ms, uint64_t* launches, int reset);
-/* the library's CUDA stream (cudaStream_t) after zkgpu_init, for event timing by the caller */
+/* the library's CUDA stream (cudaStream_t) on the primary device after zkgpu_init, for event timing by the caller */
 void* zkgpu_stream(void);
 /* number of kernel launches issued by this library in this process so far */
 uint64_t zkgpu_launch_count(void);

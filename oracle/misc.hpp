@@ -76,6 +76,8 @@ struct SmallRng : RngCore {
             s[i] = z ^ (z >> 31);
         }
     }
+    // a running generator: the four state words as rand's Xoshiro256PlusPlus holds them
+    explicit SmallRng(const u64 state[4]) { for (int i = 0; i < 4; ++i) s[i] = state[i]; }
     u64 next_u64() override {
         u64 result = rotl64(s[0] + s[3], 23) + s[0];
         u64 t = s[1] << 17;

@@ -181,6 +181,14 @@ int orc_random_fr(u64 seed, u64* out, size_t n) {
     return 0;
 }
 
+// the same from a running SmallRng (state advanced in place)
+int orc_random_fr_rng(u64* state, u64* out, size_t n) {
+    SmallRng r(state);
+    for (size_t i = 0; i < n; ++i) st(out + 4 * i, random_field<Fr>(r));
+    memcpy(state, r.s, 32);
+    return 0;
+}
+
 // SRS: format 0 = Raw, 1 = PerpetualPowersOfTau.  First call with g==NULL to get k.
 // g2s receives g2 ‖ s_g2 as 2 x (x0,x1,y0,y1) Mont-LE (32 u64).  g_lagrange is filled for Raw only.
 int orc_srs_read(const char* path, int format, unsigned* k, u64* g, u64* g_lagrange, u64* g2s) {

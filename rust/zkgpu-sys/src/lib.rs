@@ -7,7 +7,10 @@
 use std::os::raw::{c_char, c_int, c_void};
 
 extern "C" {
-    pub fn zkgpu_init(device: c_int) -> c_int;
+    /// bit i of `device_mask` selects CUDA device i; 0 = every visible device
+    pub fn zkgpu_init(device_mask: c_int) -> c_int;
+    pub fn zkgpu_device_count() -> c_int;
+    pub fn zkgpu_device_index(slot: c_int) -> c_int;
     pub fn zkgpu_shutdown();
     pub fn zkgpu_last_error() -> *const c_char;
     pub fn zkgpu_abi_version() -> c_int;
@@ -27,6 +30,8 @@ extern "C" {
     pub fn zkgpu_fft_g1(points_jacobian: *mut u64, omega: *const u64, log_n: u32) -> c_int;
     pub fn zkgpu_g_to_lagrange(g_affine: *const u64, k: u32, out_affine: *mut u64) -> c_int;
     pub fn zkgpu_params_setup(k: u32, seed: u64, g_out: *mut u64, g_lagrange_out: *mut u64) -> c_int;
+    pub fn zkgpu_params_setup_rng(k: u32, rng_state: *mut u64, g_out: *mut u64, g_lagrange_out: *mut u64) -> c_int;
+    pub fn zkgpu_fr_random_rng(rng_state: *mut u64, out: *mut u64, n: usize) -> c_int;
     pub fn zkgpu_g1_sum_affine(points_affine: *const u64, n: usize, out_affine: *mut u64) -> c_int;
     pub fn zkgpu_g1_on_curve(points_affine: *const u64, n: usize, bad_count: *mut u64) -> c_int;
 
@@ -41,9 +46,23 @@ extern "C" {
     pub fn zkgpu_prove_batch(pk: u64, advice: *const u64, instance: *const u64, num_instance: usize, m: usize,
                              rng_seeds: *const u64, proofs_out: *mut u8, proof_len: usize) -> c_int;
     pub fn zkgpu_set_rayon_threads(num_threads: u32) -> c_int;
+    /// rng_mode: RNG_SEED_U64 (tests), RNG_XOSHIRO_STATE (running SmallRng, state written back), RNG_CHACHA20_SEED (production)
+    pub fn zkgpu_prove_batch_rng(pk: u64, advice: *const u64, instance: *const u64, num_instance: usize, m: usize, rng_mode: c_int,
+                                 rng_data: *mut c_void, proofs_out: *mut u8, proof_len: usize, status_out: *mut i32) -> c_int;
+    pub fn zkgpu_prove_batch_rng_dev(pk: u64, d_advice: *const c_void, instance: *const u64, num_instance: usize, m: usize, rng_mode: c_int,
+                                     rng_data: *mut c_void, proofs_out: *mut u8, proof_len: usize, status_out: *mut i32) -> c_int;
+    /// one blocking proof; concurrent callers are coalesced into batches inside the library
+    pub fn zkgpu_prove(pk: u64, advice: *const u64, instance: *const u64, num_instance: usize, rng_mode: c_int, rng_data: *mut c_void,
+                       proof_out: *mut u8, proof_len: usize) -> c_int;
+    pub fn zkgpu_prove_stats(pk: u64, out: *mut u64) -> c_int;
     pub fn zkgpu_prove_batch_dev(pk: u64, d_advice: *const c_void, instance: *const u64, num_instance: usize, m: usize,
                                  rng_seeds: *const u64, proofs_out: *mut u8, proof_len: usize) -> c_int;
 }
+
+pub const RNG_SEED_U64: c_int = 0;
+pub const RNG_XOSHIRO_STATE: c_int = 1;
+pub const RNG_CHACHA20_SEED: c_int = 2;
+pub const ERR_WITNESS: c_int = -5;
 
 /// Panics with the library's thread-local message on a non-zero return code.
 pub fn check(rc: c_int) {

@@ -155,6 +155,25 @@ def random_fr(seed, n):
     return out
 
 
+def random_fr_rng(state, n):
+    """n x Fr::random from a running SmallRng; `state` (4,) uint64 is advanced in place"""
+    out = np.empty((n, 4), dtype=np.uint64)
+    lib().orc_random_fr_rng(_p(state), _p(out), C.c_size_t(n))
+    return out
+
+
+def smallrng_state(seed):
+    """the xoshiro256++ state of SmallRng::seed_from_u64(seed) (four SplitMix64 outputs)"""
+    st, z, mask = [], seed, (1 << 64) - 1
+    for _ in range(4):
+        z = (z + 0x9E3779B97F4A7C15) & mask
+        x = z
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & mask
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & mask
+        st.append(x ^ (x >> 31))
+    return np.array(st, dtype=np.uint64)
+
+
 def srs_read(path, fmt):
     """fmt 0 = halo2 RawBytes, 1 = .ptau.  Returns dict(k, g, g_lagrange|None, g2, s_g2)."""
     k = C.c_uint(0)
@@ -191,6 +210,17 @@ def params_setup(k, seed, threads=8):
     gl = np.empty((n, 8), dtype=np.uint64)
     g2s = np.empty((2, 16), dtype=np.uint64)
     _chk(lib().orc_params_setup(k, C.c_uint64(seed), _p(np.ascontiguousarray(gen)), threads, _p(g), _p(gl), _p(g2s)))
+    return dict(k=k, g=g, g_lagrange=gl, g2=g2s[0].copy(), s_g2=g2s[1].copy())
+
+
+def params_setup_rng(k, state, threads=8):
+    """ParamsKZG::setup(k, &mut rng) with a running SmallRng: `state` (4,) uint64 is advanced in place"""
+    n = 1 << k
+    gen = srs_read(RAW11, 0)["g2"]
+    g = np.empty((n, 8), dtype=np.uint64)
+    gl = np.empty((n, 8), dtype=np.uint64)
+    g2s = np.empty((2, 16), dtype=np.uint64)
+    _chk(lib().orc_params_setup_rng(k, _p(state), _p(np.ascontiguousarray(gen)), threads, _p(g), _p(gl), _p(g2s)))
     return dict(k=k, g=g, g_lagrange=gl, g2=g2s[0].copy(), s_g2=g2s[1].copy())
 
 
@@ -268,6 +298,14 @@ class PlonkOracle:
         stats = np.zeros(3, dtype=np.uint64)
         _chk(lib().orc_plonk_prove(self.h, _p(advice), _p(instance), C.c_size_t(instance.size // 4), C.c_uint64(seed), proof, _p(stats)))
         self.last_stats = dict(msm=int(stats[0]), ntt=int(stats[1]), ext_ntt=int(stats[2]))
+        return proof.raw
+
+    def prove_rng(self, advice, instance, mode, rng_data):
+        """create_proof with the caller's rng: mode 0 u64 seed (np.uint64 array of 1), 1 running SmallRng state ((4,) uint64,
+        advanced in place), 2 ChaCha20 seed (32 bytes as a uint8 array)"""
+        advice, instance = np.ascontiguousarray(advice), np.ascontiguousarray(instance)
+        proof = C.create_string_buffer(self.proof_len)
+        _chk(lib().orc_plonk_prove_rng(self.h, _p(advice), _p(instance), C.c_size_t(instance.size // 4), int(mode), _p(rng_data), proof))
         return proof.raw
 
     def verify(self, proof: bytes, instance):

@@ -240,29 +240,6 @@ def test_lookup_circuits_match_oracle(name, k, count):
         pk.release(); params.release()
 
 
-def test_coalesced_single_proof_requests(tiny):
-    """Concurrent per-request `prove` calls (the reference hosts' call shape) served through the coalescer:
-    every caller gets the proof the oracle produces for its own witness and seed."""
-    import threading
-    from zkgpu.coalescer import ProofCoalescer
-    shape, circ, po, params, pk = tiny
-    co = ProofCoalescer(pk.prove_batch, max_batch=8, max_wait_ms=20)
-    wits = {i: circ.witness(30 + i) for i in range(12)}
-    got = {}
-
-    def client(i):
-        got[i] = co.prove(wits[i][0], wits[i][1], 900 + i)
-    ts = [threading.Thread(target=client, args=(i,)) for i in wits]
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
-    co.close()
-    assert len(co.batches) < 12
-    for i, (adv, pi) in wits.items():
-        assert got[i] == po.prove(adv, pi, seed=900 + i)
-
-
 @pytest.mark.parametrize("name,k", [("tiny", 5), ("tiny_lookup", 5), ("deposit", 15)])
 def test_extreme_circuit_sizes(name, k):
     """Smallest domain the shapes allow (k = 5: single-warp NTT tiles, 32-row scans) and a domain larger than

@@ -2,23 +2,27 @@
 // halo2_proofs would call in place of best_multiexp / best_fft / EvaluationDomain transforms, plus
 // device-resident variants for the prover pipeline and the benchmark.  No CPU fallback anywhere: if
 // CUDA is unavailable every compute call returns ZKGPU_ERR_CUDA.
-#include "../../include/zkgpu.h"
-#include "context.cuh"
+#include "api_util.hpp"
 #include "prover_kernels.cuh"
 #include "host_util.hpp"
 
 namespace zk {
 void prover_release_all();  // prover.cu
 std::atomic<uint64_t> g_launches{0};
-Context& ctx() { static Context c; return c; }
+Runtime& rt() { static Runtime r; return r; }
+Context& ctx() { Context& c = rt().primary(); c.bind(); return c; }
 thread_local std::string g_last_error;
 
 // ---- per-kernel-class timing ------------------------------------------------------------------
+// Event pools are per CUDA device (an event may only be recorded on a stream of the device it was created on);
+// zkgpu_kernel_times sums a class over the devices.
 bool g_ktime_on = false;
 namespace {
 struct KtSlot { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending; std::vector<cudaEvent_t> free_ev; double ms = 0; uint64_t launches = 0; };
-KtSlot g_kt[KT_SLOTS];
+const int KT_MAX_DEV = 16;
+KtSlot g_kt[KT_MAX_DEV][KT_SLOTS];
 std::mutex g_kt_mu;
+int kt_dev() { int d = 0; cudaGetDevice(&d); return d < KT_MAX_DEV ? d : KT_MAX_DEV - 1; }
 cudaEvent_t kt_event(KtSlot& s) {
     if (!s.free_ev.empty()) { cudaEvent_t e = s.free_ev.back(); s.free_ev.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
@@ -35,53 +39,101 @@ void kt_collect(KtSlot& s) {
 }  // namespace
 void ktime_begin(int slot, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(g_kt_mu);
-    KtSlot& s = g_kt[slot];
+    KtSlot& s = g_kt[kt_dev()][slot];
     cudaEvent_t a = kt_event(s), b = kt_event(s);
     cudaEventRecord(a, st);
     s.pending.push_back({a, b});
 }
 void ktime_end(int slot, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(g_kt_mu);
-    KtSlot& s = g_kt[slot];
+    KtSlot& s = g_kt[kt_dev()][slot];
     if (!s.pending.empty()) cudaEventRecord(s.pending.back().second, st);
     if (s.pending.size() > 4096) kt_collect(s);
 }
 
-void Context::init(int dev) {
-    std::lock_guard<std::recursive_mutex> lk(mu);
-    if (inited) {
-        ZK_REQUIRE(dev == device, "zkgpu_init: already bound to another device (one process per GPU)");
-        return;
-    }
+// zkgpu_init(device_mask): bit i selects CUDA device i; 0 selects every visible device.
+void Runtime::init(int device_mask) {
+    std::lock_guard<std::mutex> lk(init_mu);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
         throw Error(ZK_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libzkgpu has no CPU fallback)");
-    ZK_REQUIRE(dev >= 0 && dev < count, "zkgpu_init: bad device index");
-    ZK_CUDA(cudaSetDevice(dev));
-    cudaDeviceProp prop;
-    ZK_CUDA(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major < 10)
-        throw Error(ZK_ERR_CUDA, std::string("device is ") + prop.name + " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
-                                     "); libzkgpu is built for sm_100a only");
-    ZK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    device = dev; sm_count = prop.multiProcessorCount; inited = true;
+    if (count > 30) count = 30;
+    unsigned mask = device_mask == 0 ? ((1u << count) - 1) : (unsigned)device_mask;
+    ZK_REQUIRE(device_mask >= 0 && (mask >> count) == 0, "zkgpu_init: device_mask selects a device that does not exist");
+    if (inited) {
+        unsigned cur = 0;
+        for (auto& d : devs) cur |= 1u << d->device;
+        ZK_REQUIRE(cur == mask, "zkgpu_init: already initialised with another device mask (zkgpu_shutdown first)");
+        return;
+    }
+    std::vector<std::unique_ptr<Context>> sel;
+    for (int dev = 0; dev < count; ++dev) {
+        if (!((mask >> dev) & 1)) continue;
+        ZK_CUDA(cudaSetDevice(dev));
+        cudaDeviceProp prop;
+        ZK_CUDA(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major < 10)
+            throw Error(ZK_ERR_CUDA, std::string("device is ") + prop.name + " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                         "); libzkgpu is built for sm_100a only");
+        std::unique_ptr<Context> c(new Context);
+        c->device = dev; c->slot = (int)sel.size(); c->sm_count = prop.multiProcessorCount;
+        ZK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        sel.push_back(std::move(c));
+    }
+    // peer access between the selected devices: partial results of a point-sharded MSM are summed over NVLink
+    for (auto& a : sel)
+        for (auto& b : sel) {
+            if (a->device == b->device) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, a->device, b->device) == cudaSuccess && can) {
+                cudaSetDevice(a->device);
+                cudaError_t pe = cudaDeviceEnablePeerAccess(b->device, 0);
+                if (pe != cudaSuccess) cudaGetLastError();   // already enabled by the host application: fine
+            }
+        }
+    ZK_CUDA(cudaSetDevice(sel[0]->device));
+    devs = std::move(sel);
+    inited = true;
 }
-void Context::require() {
-    if (!inited) init(0);
-    ZK_CUDA(cudaSetDevice(device));
+void Runtime::require() {
+    if (!inited) init(1);
 }
-void Context::shutdown() {
+Context* Runtime::by_cuda_index(int dev) {
+    require();
+    for (auto& d : devs) if (d->device == dev) return d.get();
+    return nullptr;
+}
+Context& Runtime::of_pointer(const void* device_ptr) {
+    require();
+    cudaPointerAttributes at;
+    ZK_CUDA(cudaPointerGetAttributes(&at, device_ptr));
+    ZK_REQUIRE(at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged, "expected a device pointer");
+    Context* c = by_cuda_index(at.device);
+    ZK_REQUIRE(c != nullptr, "device pointer belongs to a CUDA device that zkgpu_init did not select");
+    return *c;
+}
+void Context::release_all() {
     std::lock_guard<std::recursive_mutex> lk(mu);
-    if (!inited) return;
+    cudaSetDevice(device);
     cudaStreamSynchronize(stream);
-    prover_release_all();
     srs.clear();
     ws = MsmWorkspace();
     fr_buf.release(); fr_scratch.release(); pt_buf.release(); xyzz_buf.release(); aff_buf.release();
-    ntt_clear_cache();
     cudaStreamDestroy(stream);
-    inited = false; device = -1;
+    stream = nullptr;
+}
+void Runtime::shutdown() {
+    std::lock_guard<std::mutex> lk(init_mu);
+    if (!inited) return;
+    prover_release_all();
+    {
+        std::unique_lock<std::shared_mutex> tl(tab_mu);
+        for (auto& d : devs) d->release_all();
+    }
+    ntt_clear_cache();
+    devs.clear();
+    inited = false;
 }
 
 SrsEntry& Context::get_srs(uint64_t h) {
@@ -119,15 +171,10 @@ static void jacobian_out(const g1_affine_t& a, uint64_t out[12]) {
 
 using namespace zk;
 
-#define API_BEGIN try { std::lock_guard<std::recursive_mutex> lk_(ctx().mu);
-#define API_END                                                           \
-    return ZKGPU_OK; }                                                    \
-    catch (const zk::Error& e) { g_last_error = e.what(); return e.code; } \
-    catch (const std::exception& e) { g_last_error = e.what(); return ZKGPU_ERR_INTERNAL; }
 
 extern "C" {
 
-int zkgpu_abi_version(void) { return 2; }
+int zkgpu_abi_version(void) { return 3; }
 const char* zkgpu_last_error(void) { return g_last_error.c_str(); }
 uint64_t zkgpu_launch_count(void) { return g_launches.load(); }
 
@@ -135,22 +182,31 @@ void zkgpu_kernel_timing(int enable) { g_ktime_on = enable != 0; }
 int zkgpu_kernel_times(int slot, double* total_ms, uint64_t* launches, int reset) {
     if (slot < 0 || slot >= KT_SLOTS) return ZKGPU_ERR_ARG;
     std::lock_guard<std::mutex> lk(g_kt_mu);
-    kt_collect(g_kt[slot]);
-    if (total_ms) *total_ms = g_kt[slot].ms;
-    if (launches) *launches = g_kt[slot].launches;
-    if (reset) { g_kt[slot].ms = 0; g_kt[slot].launches = 0; }
+    double ms = 0; uint64_t cnt = 0;
+    int cur = 0; cudaGetDevice(&cur);
+    for (int d = 0; d < KT_MAX_DEV; ++d) {
+        KtSlot& s = g_kt[d][slot];
+        if (!s.pending.empty()) { cudaSetDevice(d); kt_collect(s); }
+        ms += s.ms; cnt += s.launches;
+        if (reset) { s.ms = 0; s.launches = 0; }
+    }
+    cudaSetDevice(cur);
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = cnt;
     return ZKGPU_OK;
 }
-void* zkgpu_stream(void) { return ctx().inited ? (void*)ctx().stream : nullptr; }
+void* zkgpu_stream(void) { return rt().inited ? (void*)rt().devs[0]->stream : nullptr; }
 
-int zkgpu_init(int device) {
-    API_BEGIN
-    ctx().init(device);
+int zkgpu_init(int device_mask) {
+    API_TRY
+    rt().init(device_mask);
     API_END
 }
 void zkgpu_shutdown(void) {
-    try { ctx().shutdown(); } catch (...) {}
+    try { rt().shutdown(); } catch (...) {}
 }
+int zkgpu_device_count(void) { return rt().inited ? (int)rt().devs.size() : 0; }
+int zkgpu_device_index(int slot) { return rt().inited && slot >= 0 && slot < (int)rt().devs.size() ? rt().devs[slot]->device : -1; }
 
 int zkgpu_msm_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint64_t out_jacobian[12]) {
     API_BEGIN
@@ -172,32 +228,41 @@ int zkgpu_msm_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint6
 }
 
 int zkgpu_srs_register(const uint64_t* g, const uint64_t* g_lagrange, uint32_t k, uint64_t* handle_out) {
-    API_BEGIN
-    Context& C = ctx(); C.require();
+    API_TRY
     ZK_REQUIRE(g && g_lagrange && handle_out, "null pointer");
     ZK_REQUIRE(k >= 1 && k <= 20, "srs: k out of range");
-    std::unique_ptr<SrsEntry> S(new SrsEntry);
-    S->k = k; S->n = (size_t)1 << k;
-    S->plan = msm_plan(S->n, true);
-    S->plan.tstride = S->n;
-    cudaStream_t st = C.stream;
-    C.pt_buf.ensure(S->n);
-    const uint64_t* src[2] = {g, g_lagrange};
-    for (int b = 0; b < 2; ++b) {
-        S->table[b].alloc(S->n * S->plan.W);
-        ZK_CUDA(cudaMemcpyAsync(C.pt_buf.p, src[b], S->n * 64, cudaMemcpyHostToDevice, st));
-        msm_precompute_table(S->plan, C.pt_buf.p, S->table[b].p, st);
+    Runtime& R = rt(); R.require();
+    uint64_t h;
+    { std::unique_lock<std::shared_mutex> tl(R.tab_mu); h = R.next_handle++; }
+    // one replica per selected device (the SRS is <= 1 MiB at k = 13, its window tables ~10 MiB per basis)
+    for (auto& dp : R.devs) {
+        DeviceScope scope(*dp);
+        Context& C = *dp;
+        std::unique_ptr<SrsEntry> S(new SrsEntry);
+        S->k = k; S->n = (size_t)1 << k;
+        S->plan = msm_plan(S->n, true);
+        S->plan.tstride = S->n;
+        cudaStream_t st = C.stream;
+        C.pt_buf.ensure(S->n);
+        const uint64_t* src[2] = {g, g_lagrange};
+        for (int b = 0; b < 2; ++b) {
+            S->table[b].alloc(S->n * S->plan.W);
+            ZK_CUDA(cudaMemcpyAsync(C.pt_buf.p, src[b], S->n * 64, cudaMemcpyHostToDevice, st));
+            msm_precompute_table(S->plan, C.pt_buf.p, S->table[b].p, st);
+        }
+        ZK_CUDA(cudaStreamSynchronize(st));
+        std::unique_lock<std::shared_mutex> tl(R.tab_mu);
+        C.srs[h] = std::move(S);
     }
-    ZK_CUDA(cudaStreamSynchronize(st));
-    uint64_t h = C.next_handle++;
-    C.srs[h] = std::move(S);
     *handle_out = h;
     API_END
 }
 int zkgpu_srs_release(uint64_t h) {
-    API_BEGIN
-    Context& C = ctx();
-    ZK_REQUIRE(C.srs.erase(h) == 1, "unknown SRS handle");
+    API_TRY
+    Runtime& R = rt(); R.require();
+    size_t erased = 0;
+    for (auto& dp : R.devs) { DeviceScope scope(*dp); std::unique_lock<std::shared_mutex> tl(R.tab_mu); erased += dp->srs.erase(h); }
+    ZK_REQUIRE(erased > 0, "unknown SRS handle");
     API_END
 }
 
@@ -223,12 +288,15 @@ int zkgpu_msm_g1_srs(uint64_t srs, int basis, const uint64_t* scalars, size_t n,
     return ZKGPU_OK;
 }
 int zkgpu_msm_g1_srs_batch_dev(uint64_t srs, int basis, const void* d_scalars, size_t n, size_t m, void* d_out_affine, void* stream) {
-    API_BEGIN
-    Context& C = ctx(); C.require();
+    API_TRY
+    ZK_REQUIRE(d_scalars && d_out_affine, "null pointer");
+    DeviceScope scope(rt().of_pointer(d_scalars));
+    Context& C = scope.C;
     SrsEntry& S = C.get_srs(srs);
     cudaStream_t st = stream ? (cudaStream_t)stream : C.stream;
     C.msm_srs_dev(S, basis, (const fr_t*)d_scalars, n, m, (g1_affine_t*)d_out_affine, st);
-    if (!stream) ZK_CUDA(cudaStreamSynchronize(st));
+    // the device's shared MSM workspace is reused by the next call (possibly on another stream): finish before the lock drops
+    ZK_CUDA(cudaStreamSynchronize(st));
     API_END
 }
 
@@ -259,9 +327,10 @@ int zkgpu_ntt_fr_batch(uint64_t* a, const uint64_t omega[4], uint32_t log_n, siz
 int zkgpu_ntt_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_n) { return zkgpu_ntt_fr_batch(a, omega, log_n, 1); }
 
 int zkgpu_ntt_fr_batch_dev(void* d_a, const uint64_t omega[4], uint32_t log_n, size_t m, void* d_scratch, void* stream) {
-    API_BEGIN
-    Context& C = ctx(); C.require();
+    API_TRY
     ZK_REQUIRE(d_a && omega, "null pointer");
+    DeviceScope scope(rt().of_pointer(d_a));
+    Context& C = scope.C;
     fr_t w; memcpy(w.l, omega, 32);
     cudaStream_t st = stream ? (cudaStream_t)stream : C.stream;
     NttJob J;
@@ -271,7 +340,8 @@ int zkgpu_ntt_fr_batch_dev(void* d_a, const uint64_t omega[4], uint32_t log_n, s
         J.scratch = C.fr_scratch.p;
     }
     ntt_run(J, st);
-    if (!stream) ZK_CUDA(cudaStreamSynchronize(st));
+    // same reason as above when the library's scratch was used; a caller-supplied scratch keeps the call asynchronous
+    if (!stream || !d_scratch) ZK_CUDA(cudaStreamSynchronize(st));
     API_END
 }
 
@@ -346,15 +416,11 @@ int zkgpu_fr_vec_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out,
 }
 int zkgpu_fr_to_mont(const uint64_t* canonical, uint64_t* out, size_t n) { return zkgpu_fr_vec_op(3, canonical, nullptr, out, n); }
 int zkgpu_fr_from_mont(const uint64_t* mont, uint64_t* out, size_t n) { return zkgpu_fr_vec_op(4, mont, nullptr, out, n); }
-/* out[i] = Fr::random(rng) for rng = SmallRng::seed_from_u64(seed) (eight next_u64 each, 512-bit reduction) */
-int zkgpu_fr_random(uint64_t seed, uint64_t* out, size_t n) {
-    API_BEGIN
-    Context& C = ctx(); C.require();
-    ZK_REQUIRE(out || n == 0, "null pointer");
-    if (n == 0) return ZKGPU_OK;
+/* out[i] = Fr::random(rng) (eight next_u64 each, 512-bit reduction) */
+static void fr_random_from(SmallRng& rng, uint64_t* out, size_t n) {
+    Context& C = ctx();
     cudaStream_t st = C.stream;
     std::vector<uint64_t> raw(8 * n);
-    SmallRng rng(seed);
     for (size_t i = 0; i < 8 * n; ++i) raw[i] = rng.next_u64();
     C.fr_buf.ensure(3 * n);
     uint64_t* d_raw = reinterpret_cast<uint64_t*>(C.fr_buf.p + n);
@@ -362,6 +428,24 @@ int zkgpu_fr_random(uint64_t seed, uint64_t* out, size_t n) {
     launch_reduce_wide(d_raw, C.fr_buf.p, n, st);
     ZK_CUDA(cudaMemcpyAsync(out, C.fr_buf.p, n * 32, cudaMemcpyDeviceToHost, st));
     ZK_CUDA(cudaStreamSynchronize(st));
+}
+/* rng = SmallRng::seed_from_u64(seed) */
+int zkgpu_fr_random(uint64_t seed, uint64_t* out, size_t n) {
+    API_BEGIN
+    ZK_REQUIRE(out || n == 0, "null pointer");
+    if (n == 0) return ZKGPU_OK;
+    SmallRng rng(seed);
+    fr_random_from(rng, out, n);
+    API_END
+}
+/* rng = the caller's running SmallRng (xoshiro256++ state, advanced in place) */
+int zkgpu_fr_random_rng(uint64_t rng_state[4], uint64_t* out, size_t n) {
+    API_BEGIN
+    ZK_REQUIRE(rng_state && (out || n == 0), "null pointer");
+    if (n == 0) return ZKGPU_OK;
+    SmallRng rng(rng_state);
+    fr_random_from(rng, out, n);
+    memcpy(rng_state, rng.s, 32);
     API_END
 }
 

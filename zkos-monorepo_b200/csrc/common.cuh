@@ -35,7 +35,7 @@ extern std::atomic<uint64_t> g_launches;  // kernels launched by this library (z
 
 // Optional per-kernel-class device timing (zkgpu_kernel_timing): CUDA events recorded on the launching stream
 // around the launches of one class; read back with zkgpu_kernel_times.  Off by default (no events recorded).
-enum { KT_MSM_BUCKETS = 0, KT_MSM_SORT = 1, KT_MSM_REDUCE = 2, KT_NTT = 3, KT_EVAL_H = 4, KT_PERM = 5, KT_POLY = 6, KT_SLOTS = 8 };
+enum { KT_MSM_BUCKETS = 0, KT_MSM_SORT = 1, KT_MSM_REDUCE = 2, KT_NTT = 3, KT_EVAL_H = 4, KT_PERM = 5, KT_POLY = 6, KT_LOOKUP = 7, KT_MISC = 8, KT_SLOTS = 10 };
 extern bool g_ktime_on;
 void ktime_begin(int slot, cudaStream_t st);
 void ktime_end(int slot, cudaStream_t st);
@@ -67,5 +67,19 @@ struct DevBuf {
 };
 
 static inline unsigned ceil_div(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// Kernel attributes (cudaFuncSetAttribute) belong to one device: run `fn` once for every CUDA device of this process a
+// kernel is launched on.  The current device is the launching thread's.
+struct DeviceOnce {
+    std::atomic<uint64_t> done{0};
+    template <class F> void run(F fn) {
+        int dev = 0;
+        ZK_CUDA(cudaGetDevice(&dev));
+        const uint64_t bit = 1ull << (dev & 63);
+        if (done.load(std::memory_order_acquire) & bit) return;
+        fn();   // idempotent: two threads racing here both set the same attribute
+        done.fetch_or(bit, std::memory_order_release);
+    }
+};
 
 }  // namespace zk

@@ -95,7 +95,13 @@ struct Transcript {
     }
 };
 
-// ---- SmallRng (xoshiro256++) -------------------------------------------------------------------
+// ---- proof RNGs ---------------------------------------------------------------------------------
+// `generate_proof(.., rng: &mut impl RngCore)` (/root/reference/crates/shielder_bindings/src/circuits/mod.rs:103-111) is called
+// with a running `SmallRng` in the seeded tests (/root/reference/crates/halo2-verifier/src/generator.rs:117-130) and with
+// `OsRng` / `thread_rng()` in production (/root/reference/crates/shielder-account/src/call_data.rs:499,
+// /root/reference/crates/shielder_bindings/src/circuits/deposit.rs:108).  ProofRng is the `RngCore` the prover draws from:
+//   xoshiro256++ (rand 0.8.5 SmallRng on 64-bit targets) from a u64 seed or from a caller-owned running state, or
+//   ChaCha20 (rand_chacha 0.3.1 ChaCha20Rng::from_seed) from 32 bytes of caller entropy.
 struct SmallRng {
     uint64_t s[4];
     explicit SmallRng(uint64_t seed) {
@@ -107,6 +113,7 @@ struct SmallRng {
             s[i] = z ^ (z >> 31);
         }
     }
+    explicit SmallRng(const uint64_t state[4]) { memcpy(s, state, 32); }
     uint64_t next_u64() {
         uint64_t r = rotl64_(s[0] + s[3], 23) + s[0];
         uint64_t t = s[1] << 17;
@@ -114,10 +121,54 @@ struct SmallRng {
         s[2] ^= t; s[3] = rotl64_(s[3], 45);
         return r;
     }
+};
+
+// rand_chacha 0.3.1 ChaCha20Rng: key = seed, 64-bit block counter in words 12-13, stream id 0; output words in block order.
+struct ChaCha20Host {
+    uint32_t key[8]; uint64_t counter = 0; uint32_t buf[16]; unsigned idx = 16;
+    explicit ChaCha20Host(const uint8_t seed[32]) { memcpy(key, seed, 32); }
+    static inline uint32_t rotl(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+    void refill() {
+        uint32_t st[16] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574};
+        for (int i = 0; i < 8; ++i) st[4 + i] = key[i];
+        st[12] = (uint32_t)counter; st[13] = (uint32_t)(counter >> 32); st[14] = 0; st[15] = 0;
+        uint32_t x[16]; memcpy(x, st, 64);
+        auto qr = [&](int a, int b, int c, int d) {
+            x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 12);
+            x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7);
+        };
+        for (int r = 0; r < 10; ++r) {
+            qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
+            qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
+        }
+        for (int i = 0; i < 16; ++i) buf[i] = x[i] + st[i];
+        ++counter; idx = 0;
+    }
+    uint32_t next_u32() { if (idx >= 16) refill(); return buf[idx++]; }
+    uint64_t next_u64() { uint64_t lo = next_u32(), hi = next_u32(); return lo | (hi << 32); }
+};
+
+enum { RNG_SEED_U64 = 0, RNG_XOSHIRO_STATE = 1, RNG_CHACHA20_SEED = 2 };
+static inline size_t rng_data_stride(int mode) { return mode == RNG_SEED_U64 ? 8 : 32; }
+
+struct ProofRng {
+    int mode;
+    SmallRng xo;
+    ChaCha20Host cc;
+    static const uint8_t* zero32() { static const uint8_t z[32] = {0}; return z; }
+    ProofRng(int mode_, const uint8_t* data)
+        : mode(mode_), xo((uint64_t)0), cc(mode_ == RNG_CHACHA20_SEED ? data : zero32()) {
+        if (mode == RNG_SEED_U64) { uint64_t seed; memcpy(&seed, data, 8); xo = SmallRng(seed); }
+        else if (mode == RNG_XOSHIRO_STATE) { uint64_t st[4]; memcpy(st, data, 32); xo = SmallRng(st); }
+    }
+    uint64_t next_u64() { return mode == RNG_CHACHA20_SEED ? cc.next_u64() : xo.next_u64(); }
     // `Fr::random` consumes eight u64 (from_u512); the reduction is done on the device
     void next_wide(uint64_t out[8]) { for (int i = 0; i < 8; ++i) out[i] = next_u64(); }
     void skip_wide() { for (int i = 0; i < 8; ++i) next_u64(); }
+    // RngCore::fill_bytes of 32 bytes: four next_u64 (xoshiro) / eight output words (ChaCha block rng) — the same bytes
     void fill_bytes32(uint8_t out[32]) { for (int i = 0; i < 4; ++i) { uint64_t v = next_u64(); memcpy(out + 8 * i, &v, 8); } }
+    // running state handed back to the caller (xoshiro state mode): the host's rng continues where the proof stopped
+    void store_state(uint8_t* data) const { if (mode == RNG_XOSHIRO_STATE) memcpy(data, xo.s, 32); }
 };
 
 }  // namespace zk

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(128) k_lookup_compress(const LookupCompressArg
 }
 void launch_lookup_compress(const LookupCompressArgs& a, fr_t* out_in, fr_t* out_tab, size_t B, cudaStream_t st) {
     size_t total = (B * a.lp.L) << a.k;
+    KtScope kt(KT_LOOKUP, st);
     if (total) ZK_LAUNCH(k_lookup_compress, ceil_div(total, 128), 128, 0, st, a, out_in, out_tab, B);
 }
 
@@ -120,7 +121,7 @@ __device__ uint32_t block_exclusive_scan(uint32_t* v, unsigned n, uint32_t* part
 
 // one CTA per (proof, lookup).  sort_a / sort_t hold the sorted canonical columns.
 __global__ void __launch_bounds__(1024) k_lookup_permute(const fr_t* sort_a, fr_t* sort_t, fr_t* perm_in, fr_t* perm_tab, unsigned k,
-                                                         unsigned usable, int* d_error) {
+                                                         unsigned usable, unsigned L, int* d_error /*[B], per proof*/) {
     extern __shared__ uint32_t sm[];
     const unsigned n = 1u << k;
     uint32_t* rep = sm;            // [n] 1 if the row repeats the previous input value -> exclusive scan
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(1024) k_lookup_permute(const fr_t* sort_a, fr_
         fr_t v = fe_load(A + r);
         unsigned lo = 0, hi = usable;   // lower_bound of v in T[0, usable)
         while (lo < hi) { unsigned mid = (lo + hi) >> 1; if (lt256(fe_load(T + mid), v)) lo = mid + 1; else hi = mid; }
-        if (lo >= usable || !(fe_load(T + lo) == v)) atomicExch(d_error, 1);
+        if (lo >= usable || !(fe_load(T + lo) == v)) atomicExch(d_error + blockIdx.x / L, 1);
         else keep[lo] = 0;              // distinct values hit distinct positions
     }
     __syncthreads();
@@ -166,15 +167,16 @@ __global__ void __launch_bounds__(1024) k_lookup_permute(const fr_t* sort_a, fr_
 }
 
 void launch_lookup_permute(const fr_t* comp_in, const fr_t* comp_tab, fr_t* perm_in, fr_t* perm_tab, fr_t* sort_a, fr_t* sort_t, unsigned k,
-                           size_t usable, size_t BL, int* d_error, cudaStream_t st) {
+                           size_t usable, size_t BL, unsigned L, int* d_error, cudaStream_t st) {
     if (!BL) return;
     const unsigned n = 1u << k;
     unsigned threads = n / 2 < 1024 ? (n / 2 < 32 ? 32 : n / 2) : 1024;
+    KtScope kt(KT_LOOKUP, st);
     ZK_LAUNCH(k_lookup_sort, (unsigned)(2 * BL), threads, 0, st, comp_in, comp_tab, sort_a, sort_t, k, (unsigned)usable, BL);
     size_t smem = ((size_t)2 * n + threads) * sizeof(uint32_t);
-    static std::once_flag attr_once;   // two pipeline workers may arrive here together
-    std::call_once(attr_once, [] { ZK_CUDA(cudaFuncSetAttribute(k_lookup_permute, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); });
-    ZK_LAUNCH(k_lookup_permute, (unsigned)BL, threads, smem, st, sort_a, sort_t, perm_in, perm_tab, k, (unsigned)usable, d_error);
+    static DeviceOnce attr_once;   // per device; two pipeline workers may arrive here together
+    attr_once.run([] { ZK_CUDA(cudaFuncSetAttribute(k_lookup_permute, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); });
+    ZK_LAUNCH(k_lookup_permute, (unsigned)BL, threads, smem, st, sort_a, sort_t, perm_in, perm_tab, k, (unsigned)usable, L, d_error);
 }
 
 __global__ void __launch_bounds__(128) k_lookup_num_den(const fr_t* comp_in, const fr_t* comp_tab, const fr_t* perm_in, const fr_t* perm_tab,

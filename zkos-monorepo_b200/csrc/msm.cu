@@ -93,7 +93,7 @@ __global__ void k_msm_scatter(const fr_t* __restrict__ scalars, size_t total, Ms
     for_each_digit(s.l, D.c, D.W, [&](unsigned w, uint32_t mag, bool negative) {
         unsigned g = D.precomp ? 0 : w;
         size_t key = (size_t)g * D.nb + (mag - 1);
-        uint32_t pos = atomicSub(cm + key, 1u) - 1;  // leaves the histogram zeroed for the next call
+        uint32_t pos = atomicSub(cm + key, 1u) - 1;
         uint32_t ref = D.precomp ? w * D.tstride + i : i;
         em[om[key] + pos] = ref | (negative ? 0x80000000u : 0u);
     });
@@ -562,10 +562,7 @@ MsmPlan msm_plan(size_t n, bool precomp, unsigned force_c) {
 
 void MsmWorkspace::ensure(const MsmPlan& p, size_t M) {
     size_t K = p.K();
-    if (counts.n < M * K) {
-        counts.alloc(M * K);
-        ZK_CUDA(cudaMemset(counts.p, 0, counts.bytes()));
-    }
+    counts.ensure(M * K);
     offsets.ensure(M * (K + 1));
     entries.ensure(M * p.entries_per_msm());
     buckets.ensure(M * K);
@@ -602,11 +599,14 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
     const size_t sort_smem = (K + 1024 + D.heavy + 2) * sizeof(uint32_t);
     if (K <= 8192 && plan.n <= (1u << 20) && M >= 32) {   // one CTA per MSM: needs enough MSMs to fill the GPU
         KtScope kt(KT_MSM_SORT, st);
-        static std::once_flag sort_once;
-        std::call_once(sort_once, [] { ZK_CUDA(cudaFuncSetAttribute(k_msm_sort_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); });
+        static DeviceOnce sort_once;
+        sort_once.run([] { ZK_CUDA(cudaFuncSetAttribute(k_msm_sort_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); });
         ZK_LAUNCH(k_msm_sort_smem, (unsigned)M, 1024, sort_smem, st, d_scalars, D, ws.offsets.p, ws.entries.p, ws.order.p);
     } else {
         KtScope kt(KT_MSM_SORT, st);
+        // the histogram is zeroed on the launching stream every call (k_msm_scatter counts it back down to zero, but a fresh
+        // allocation or a call that failed between the two kernels must not leak into this one)
+        ZK_CUDA(cudaMemsetAsync(ws.counts.p, 0, M * K * sizeof(uint32_t), st));
         ZK_LAUNCH(k_msm_count, ceil_div(total, 256), 256, 0, st, d_scalars, total, D, ws.counts.p);
         unsigned scan_threads = K >= 1024 ? 1024 : 32;
         while (scan_threads < K && scan_threads < 1024) scan_threads <<= 1;
@@ -643,8 +643,8 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
     unsigned Tmax = M * plan.G < 148 * 4 ? ZK_REDUCE_T_LAT : reduce_t;
     unsigned T = plan.nb < Tmax ? plan.nb : Tmax;
     g1_xyzz_t* groups = plan.precomp ? d_out : ws.groups.p;
-    static std::once_flag reduce_once;
-    std::call_once(reduce_once, [] { ZK_CUDA(cudaFuncSetAttribute(k_msm_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, ZK_REDUCE_T_LAT * (int)sizeof(g1_xyzz_t))); });
+    static DeviceOnce reduce_once;
+    reduce_once.run([] { ZK_CUDA(cudaFuncSetAttribute(k_msm_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, ZK_REDUCE_T_LAT * (int)sizeof(g1_xyzz_t))); });
     ZK_LAUNCH(k_msm_reduce, (unsigned)(M * plan.G), T, T * sizeof(g1_xyzz_t), st, ws.buckets.p, D, groups);
     if (!plan.precomp) {
         ZK_LAUNCH(k_msm_combine, ceil_div(M, 64), 64, 0, st, ws.groups.p, D, M, d_out);
@@ -658,6 +658,7 @@ void msm_precompute_table(const MsmPlan& plan, const g1_affine_t* d_bases, g1_af
 
 void g1_normalize(const g1_xyzz_t* d_in, g1_affine_t* d_out, size_t m, cudaStream_t st) {
     if (!m) return;
+    KtScope kt(KT_MISC, st);
     ZK_LAUNCH(k_normalize, ceil_div(m, 64), 64, 0, st, d_in, d_out, m);
 }
 

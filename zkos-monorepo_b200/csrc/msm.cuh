@@ -22,7 +22,7 @@ struct MsmPlan {
 MsmPlan msm_plan(size_t n, bool precomp, unsigned force_c = 0);
 
 struct MsmWorkspace {
-    DevBuf<uint32_t> counts;    // M * K      (zero between calls)
+    DevBuf<uint32_t> counts;    // M * K      (zeroed on the stream by every call that uses it)
     DevBuf<uint32_t> offsets;   // M * (K+1)
     DevBuf<uint32_t> entries;   // M * n * W
     DevBuf<g1_xyzz_t> buckets;  // M * K

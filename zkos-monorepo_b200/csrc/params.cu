@@ -4,8 +4,7 @@
 // g_lagrange = g_to_lagrange(g) (K6, g1fft.cu).  The production SRS comes from the ppot ceremony files
 // through crates/powers-of-tau instead; k = 13 of that ceremony is not in the reference tree
 // (.MISSING_LARGE_BLOBS), which is why the benchmark uses this setup.
-#include "../../include/zkgpu.h"
-#include "context.cuh"
+#include "api_util.hpp"
 #include "host_util.hpp"
 
 namespace zk {
@@ -36,8 +35,8 @@ using namespace zk;
 
 extern "C" int zkgpu_g1_on_curve(const uint64_t* points_affine, size_t n, uint64_t* bad_count) {
     try {
-        std::lock_guard<std::recursive_mutex> lk(ctx().mu);
-        Context& C = ctx(); C.require();
+        DeviceScope api_scope_(rt().primary());
+        Context& C = api_scope_.C;
         ZK_REQUIRE((points_affine || n == 0) && bad_count, "null pointer");
         *bad_count = 0;
         if (!n) return ZKGPU_OK;
@@ -56,17 +55,17 @@ extern "C" int zkgpu_g1_on_curve(const uint64_t* points_affine, size_t n, uint64
     catch (const std::exception& e) { g_last_error = e.what(); return ZKGPU_ERR_INTERNAL; }
 }
 
-extern "C" int zkgpu_params_setup(uint32_t k, uint64_t seed, uint64_t* g_out, uint64_t* g_lagrange_out) {
+static int params_setup_impl(uint32_t k, SmallRng& rng, uint64_t* g_out, uint64_t* g_lagrange_out) {
     try {
-        std::lock_guard<std::recursive_mutex> lk(ctx().mu);
-        Context& C = ctx(); C.require();
+        DeviceScope api_scope_(rt().primary());
+        Context& C = api_scope_.C;
         ZK_REQUIRE(g_out, "null pointer");
         ZK_REQUIRE(k >= 1 && k <= 24 && (k <= 20 || !g_lagrange_out), "params_setup: k out of range (g_lagrange up to 2^20)");
         const size_t n = (size_t)1 << k;
         cudaStream_t st = C.stream;
         // s = Fr::random(rng) = from_u512 of eight next_u64
-        SmallRng rng(seed);
-        uint64_t w[8]; rng.next_wide(w);
+        uint64_t w[8];
+        for (int i = 0; i < 8; ++i) w[i] = rng.next_u64();
         fr_t lo, hi;
         for (int i = 0; i < 4; ++i) {
             lo.l[2 * i] = (uint32_t)w[i]; lo.l[2 * i + 1] = (uint32_t)(w[i] >> 32);
@@ -98,6 +97,21 @@ extern "C" int zkgpu_params_setup(uint32_t k, uint64_t seed, uint64_t* g_out, ui
         return ZKGPU_OK;
     } catch (const zk::Error& e) { g_last_error = e.what(); return e.code; }
     catch (const std::exception& e) { g_last_error = e.what(); return ZKGPU_ERR_INTERNAL; }
+}
+
+extern "C" int zkgpu_params_setup(uint32_t k, uint64_t seed, uint64_t* g_out, uint64_t* g_lagrange_out) {
+    SmallRng rng(seed);
+    return params_setup_impl(k, rng, g_out, g_lagrange_out);
+}
+// The same from a RUNNING SmallRng: `rng_state` is the caller's xoshiro256++ state; it is advanced by the one `Fr::random`
+// that `ParamsKZG::setup` draws, so the caller's stream continues exactly as the reference's does when one rng produces the
+// SRS, the witness and the proof (/root/reference/crates/halo2-verifier/src/generator.rs:117-130).
+extern "C" int zkgpu_params_setup_rng(uint32_t k, uint64_t rng_state[4], uint64_t* g_out, uint64_t* g_lagrange_out) {
+    if (!rng_state) { g_last_error = "null pointer"; return ZKGPU_ERR_ARG; }
+    SmallRng rng(rng_state);
+    int rc = params_setup_impl(k, rng, g_out, g_lagrange_out);
+    if (rc == ZKGPU_OK) memcpy(rng_state, rng.s, 32);
+    return rc;
 }
 
 // Sum of n affine points on the HOST (no GPU needed): the combine step of a point-sharded MSM, where every GPU

@@ -12,8 +12,7 @@
 // constant memory (3.8 KB, every lane reads the same word: broadcast).  Work per hash: 8 full rounds x 8 S-boxes x 4 products
 // + 48 partial rounds x (4 + 8) products = 832 Montgomery products — IMAD-bound like the rest of the prover; a batch of
 // 1024 withdraw witnesses needs 13 x 1024 hashes = 11 M products, microseconds next to the 64 G products of their proofs.
-#include "../../include/zkgpu.h"
-#include "context.cuh"
+#include "api_util.hpp"
 #include "poseidon2_consts.inc"
 
 namespace zk {
@@ -98,11 +97,6 @@ __global__ void k_merkle_check(const fr_t* __restrict__ paths, const fr_t* __res
 
 using namespace zk;
 
-#define API_BEGIN try { std::lock_guard<std::recursive_mutex> lk_(ctx().mu);
-#define API_END                                                           \
-    return ZKGPU_OK; }                                                    \
-    catch (const zk::Error& e) { g_last_error = e.what(); return e.code; } \
-    catch (const std::exception& e) { g_last_error = e.what(); return ZKGPU_ERR_INTERNAL; }
 
 extern "C" {
 
@@ -124,8 +118,11 @@ int zkgpu_poseidon2_hash_batch(const uint64_t* inputs, size_t len, size_t m, uin
 }
 
 int zkgpu_poseidon2_hash_batch_dev(const void* d_inputs, size_t len, size_t m, void* d_out, void* stream) {
-    API_BEGIN
-    Context& C = ctx(); C.require();
+    API_TRY
+    if (!m) return ZKGPU_OK;
+    ZK_REQUIRE(d_inputs && d_out, "null pointer");
+    DeviceScope scope(rt().of_pointer(d_inputs));
+    Context& C = scope.C;
     ZK_REQUIRE(len >= 1 && len <= 7, "poseidon2: input length must be between 1 and 7 (POSEIDON_RATE)");
     ZK_REQUIRE(m == 0 || (d_inputs && d_out), "null pointer");
     cudaStream_t st = stream ? (cudaStream_t)stream : C.stream;

@@ -19,8 +19,7 @@
 // (theta/beta/gamma, y, x, zeta/nu, mu) are the only host synchronisation points.
 // Witness synthesis (the circuit's own Rust code) is outside the path: the caller passes assigned
 // advice columns, as `create_proof` has them after `synthesize`.
-#include "../../include/zkgpu.h"
-#include "context.cuh"
+#include "api_util.hpp"
 #include "prover_kernels.cuh"
 #include "plonk_types.hpp"
 #include "host_util.hpp"
@@ -32,6 +31,8 @@
 #include <chrono>
 #include <thread>
 #include <exception>
+#include <deque>
+#include <condition_variable>
 
 namespace zk {
 
@@ -159,7 +160,11 @@ struct ProverWs {
     HostPinned h_aff, h_evals, h_stage;
 };
 
-struct PkEntry {
+static const unsigned BATCH_WORKERS = 3;   // pipeline workers of a zkgpu_prove_batch call
+static const unsigned COALESCE_WORKERS = 2;   // dispatcher threads (per device) behind zkgpu_prove
+struct PkEntry {   // one replica per selected device
+    Context* C = nullptr;
+    std::mutex batch_mu;   // one zkgpu_prove_batch at a time per replica (its workers own ws[0..2])
     CsDesc cs;
     uint64_t srs_handle = 0;
     unsigned k = 0, ek = 0, A = 0, F = 0, S = 0, P = 0, Q = 0, bf = 0, chunk = 0, L = 0;
@@ -180,18 +185,57 @@ struct PkEntry {
     const fr_t* ext_tw = nullptr;
     std::vector<g1_affine_t> fixed_commitments, perm_commitments;
     QueryPlan plan;
-    ProverWs ws[3];   // ws[0] also serves keygen; ws[1], ws[2] are further pipeline workers
+    ProverWs ws[BATCH_WORKERS + COALESCE_WORKERS];   // ws[0] also serves keygen; ws[3..] belong to the zkgpu_prove dispatchers
     mutable size_t cached_batch = 0;
 };
 
-static std::map<uint64_t, std::unique_ptr<PkEntry>> g_pks;
+// One blocking single-proof request (zkgpu_prove): what one tokio task of the reference's prover server holds while it waits
+// for `generate_proof` (/root/reference/tee/crates/shielder-prover-tee/src/server.rs:157-195).
+struct ProveReq {
+    const fr_t* advice; const fr_t* instance; size_t num_pi;
+    int rng_mode; uint8_t* rng_data;
+    uint8_t* proof_out;
+    int32_t status = 0;
+    int rc = 0; std::string err;
+    bool done = false;
+};
+struct PkShared;
+// Request coalescer: concurrent zkgpu_prove callers enqueue and sleep; per device, COALESCE_WORKERS dispatcher threads turn
+// whatever is waiting into one lock-step sub-batch each.  No caller ever queues on a mutex around the GPU.
+struct Coalescer {
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<ProveReq*> q;
+    unsigned idle = 0;
+    bool stop = false;
+    std::vector<std::thread> threads;
+    uint64_t batches = 0, requests = 0, max_batch_seen = 0;   // statistics (zkgpu_prove_stats)
+};
+struct PkShared {
+    std::vector<std::unique_ptr<PkEntry>> dev;   // replica per selected device, in Runtime::devs order
+    Coalescer co;
+    std::once_flag co_once;
+    ~PkShared();
+};
+
+static std::map<uint64_t, std::shared_ptr<PkShared>> g_pks;   // guarded by rt().tab_mu
 // rayon::current_num_threads() of the host being replaced: halo2's vanishing prover fills the random polynomial in chunks of
 // n / num_threads coefficients, one ChaCha20 stream (seeded from the proof's main rng, in chunk order) per chunk, so the proof bytes
 // depend on it.  1 = one stream (the `multicore` feature off); set with zkgpu_set_rayon_threads.
 static std::atomic<unsigned> g_rayon_threads{1};
 static size_t vanishing_chunk(size_t n) { unsigned t = g_rayon_threads.load(); return std::max<size_t>(1, n / (t ? t : 1)); }
 static uint64_t g_next_pk = 1;
-void prover_release_all() { g_pks.clear(); }
+void prover_release_all() {
+    std::map<uint64_t, std::shared_ptr<PkShared>> drop;
+    { std::unique_lock<std::shared_mutex> tl(rt().tab_mu); drop.swap(g_pks); }
+    drop.clear();   // joins the dispatcher threads, frees device memory
+}
+static std::shared_ptr<PkShared> find_pk(uint64_t handle) {
+    std::shared_lock<std::shared_mutex> tl(rt().tab_mu);
+    auto it = g_pks.find(handle);
+    ZK_REQUIRE(it != g_pks.end(), "unknown proving key handle");
+    return it->second;
+}
 
 static fr_t host_rotate(const PkEntry& pk, const fr_t& x, int rot) {
     if (rot >= 0) return x * fr_pow_u64(pk.omega, (uint64_t)rot);
@@ -298,6 +342,7 @@ static void trace_dev(const char* name, const fr_t* d, size_t count, size_t reps
 static std::unique_ptr<PkEntry> keygen(Context& C, uint64_t srs_handle, const uint8_t* blob, size_t len) {
     std::unique_ptr<PkEntry> pkp(new PkEntry);
     PkEntry& pk = *pkp;
+    pk.C = &C;
     pk.cs = CsDesc::parse(blob, len);
     const CsDesc& cs = pk.cs;
     SrsEntry& S = C.get_srs(srs_handle);
@@ -517,7 +562,7 @@ static void ensure_ws(PkEntry& pk, ProverWs& W, size_t B) {
         W.raw_la.ensure(BL * (pk.bf + 1) * 8); W.raw_ls.ensure(BL * (pk.bf + 1) * 8); W.raw_lz.ensure(BL * pk.bf * 8);
         W.carries.ensure(BL);
     }
-    W.d_error.ensure(1);
+    W.d_error.ensure(B);
     W.raw_adv.ensure(std::max<size_t>(1, B * pk.A * (pk.bf + 1) * 8)); W.raw_z.ensure(std::max<size_t>(1, B * pk.P * pk.bf * 8));
     W.seeds.ensure(B * 32 * ((pk.n + vanishing_chunk(pk.n) - 1) / vanishing_chunk(pk.n))); W.ch.ensure(B);
     size_t max_pts = B * std::max<size_t>(std::max<size_t>(pk.A, pk.P + pk.L + 1), std::max<size_t>(pk.Q, 2 * pk.L + 1));
@@ -525,11 +570,32 @@ static void ensure_ws(PkEntry& pk, ProverWs& W, size_t B) {
     W.h_aff.ensure(max_pts * sizeof(g1_affine_t)); W.h_evals.ensure(B * (pk.num_evals + 1) * sizeof(fr_t));
 }
 
-static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* advice, bool advice_on_device, const fr_t* instance, size_t num_pi,
-                            size_t B, const uint64_t* seeds, uint8_t* proofs, const fr_t* next_advice = nullptr, size_t next_B = 0) {
+// Per-proof status codes (include/zkgpu.h)
+enum { PROOF_OK = 0, PROOF_LOOKUP_FAILED = 1 };
+struct RngRef { int mode; uint8_t* data; };   // data: seed (u64), xoshiro state (4 x u64, written back) or ChaCha20 seed (32 B)
+// A sub-batch of B proofs of one circuit.  Advice is either one contiguous [B][A][n] block (host or device memory) or one
+// host pointer per proof (coalesced single-proof requests); everything else is contiguous.
+struct BatchView {
+    size_t B = 0, num_pi = 0;
+    const fr_t* advice = nullptr; bool advice_on_device = false;
+    const fr_t* const* advice_ptrs = nullptr;
+    const fr_t* instance = nullptr;     // [B][num_pi]
+    const RngRef* rng = nullptr;        // [B]
+    uint8_t* proofs = nullptr;          // [B][proof_len]
+    int32_t* status = nullptr;          // [B], may be null
+    // the worker's next sub-batch (contiguous host advice only): uploaded in the background
+    const fr_t* next_advice = nullptr; size_t next_B = 0;
+};
+
+static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
+    Context& C = *pk.C;
     const CsDesc& cs = pk.cs;
     if (!W.stream) ZK_CUDA(cudaStreamCreateWithFlags(&W.stream, cudaStreamNonBlocking));
     cudaStream_t st = W.stream;
+    const size_t B = V.B, num_pi = V.num_pi;
+    const fr_t* advice = V.advice; const bool advice_on_device = V.advice_on_device;
+    const fr_t* instance = V.instance; uint8_t* proofs = V.proofs;
+    const fr_t* next_advice = V.next_advice; const size_t next_B = V.next_B;
     const size_t n = pk.n, en = pk.cn /* coset-major rows per column */, A = pk.A, P = pk.P, Q = pk.Q, bf = pk.bf;
     const size_t ns = pk.plan.sets.size();
     ensure_ws(pk, W, B);
@@ -544,12 +610,14 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
     std::vector<uint64_t> raw_la(B * L * (bf + 1) * 8), raw_ls(B * L * (bf + 1) * 8), raw_lz(B * L * bf * 8);
     const size_t vchunk = vanishing_chunk(n), vnch = (n + vchunk - 1) / vchunk;
     std::vector<uint8_t> cseeds(B * vnch * 32);
+    std::vector<int32_t> status(B, PROOF_OK);
     for (size_t b = 0; b < B; ++b) {
         ps.emplace_back(proofs + b * pk.proof_len);
         ProofState& p = ps.back();
         p.tr.common_scalar(pk.digest);
         for (size_t i = 0; i < num_pi; ++i) p.tr.common_scalar(instance[b * num_pi + i]);
-        SmallRng rng(seeds[b]);
+        // The proof's whole rng stream is drawn up front, in the order create_proof draws it
+        ProofRng rng(V.rng[b].mode, V.rng[b].data);
         // advice blinding rows column by column, then one unused Blind per column
         for (size_t t = 0; t < A * (bf + 1); ++t) rng.next_wide(&raw_adv[(b * A * (bf + 1) + t) * 8]);
         for (size_t c = 0; c < A; ++c) rng.skip_wide();
@@ -569,9 +637,17 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
             for (size_t t = 0; t < bf; ++t) rng.next_wide(&raw_lz[((b * L + l) * bf + t) * 8]);
             rng.skip_wide();
         }
-        // vanishing: ChaCha20 seed for the random polynomial, its Blind; quotient piece Blinds follow (unused)
+        // vanishing: ChaCha20 seeds of the random polynomial's chunks, its Blind, then the Q quotient-piece Blinds: the
+        // last draws of create_proof (KZG ignores every Blind, SHPLONK draws nothing)
         for (size_t c = 0; c < vnch; ++c) rng.fill_bytes32(&cseeds[(b * vnch + c) * 32]);
+        rng.skip_wide();
+        for (size_t i = 0; i < Q; ++i) rng.skip_wide();
+        rng.store_state(V.rng[b].data);   // a running SmallRng continues after the proof, as `&mut rng` does upstream
     }
+    if (V.advice_ptrs) {
+        for (size_t b = 0; b < B; ++b)
+            ZK_CUDA(cudaMemcpyAsync(W.adv.p + b * A * n, V.advice_ptrs[b], A * n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+    } else
     if (advice_on_device) ZK_CUDA(cudaMemcpyAsync(W.adv.p, advice, B * A * n * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
     else if (W.prefetched_src == advice) {
         // uploaded while the previous sub-batch was computing: take the staging buffer
@@ -596,7 +672,7 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
     if (num_pi)
         ZK_CUDA(cudaMemcpy2DAsync(W.inst.p, n * sizeof(fr_t), instance, num_pi * sizeof(fr_t), num_pi * sizeof(fr_t), B, cudaMemcpyHostToDevice, st));
     h2d(W.raw_adv.p, raw_adv, st); h2d(W.raw_z.p, raw_z, st); h2d(W.seeds.p, cseeds, st);
-    if (L) { h2d(W.raw_la.p, raw_la, st); h2d(W.raw_ls.p, raw_ls, st); h2d(W.raw_lz.p, raw_lz, st); ZK_CUDA(cudaMemsetAsync(W.d_error.p, 0, sizeof(int), st)); }
+    if (L) { h2d(W.raw_la.p, raw_la, st); h2d(W.raw_ls.p, raw_ls, st); h2d(W.raw_lz.p, raw_lz, st); ZK_CUDA(cudaMemsetAsync(W.d_error.p, 0, B * sizeof(int), st)); }
 
     auto fetch_points = [&](size_t count) -> const g1_affine_t* {
         ZK_CUDA(cudaMemcpyAsync(W.h_aff.p, W.aff.p, count * sizeof(g1_affine_t), cudaMemcpyDeviceToHost, st));
@@ -630,17 +706,20 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
         la.adv = W.adv.p; la.adv_proof_stride = A * n; la.inst = W.inst.p; la.inst_proof_stride = n; la.fixed_vals = pk.fixed_vals.p;
         la.ch = W.ch.p; la.lp = lookup_progs(pk); la.k = pk.k;
         launch_lookup_compress(la, W.lk_in.p, W.lk_tab.p, B, st);
-        launch_lookup_permute(W.lk_in.p, W.lk_tab.p, W.lk_a.p, W.lk_s.p, W.sort_a.p, W.sort_t.p, pk.k, pk.ustart, B * L, W.d_error.p, st);
+        launch_lookup_permute(W.lk_in.p, W.lk_tab.p, W.lk_a.p, W.lk_s.p, W.sort_a.p, W.sort_t.p, pk.k, pk.ustart, B * L, (unsigned)L, W.d_error.p, st);
         launch_scatter_random(W.lk_a.p, L * n, n, pk.ustart, W.raw_la.p, B, L, bf + 1, st);
         launch_scatter_random(W.lk_s.p, L * n, n, pk.ustart, W.raw_ls.p, B, L, bf + 1, st);
         trace_dev("lookup_permuted_input", W.lk_a.p, n, L, n, st);
         trace_dev("lookup_permuted_table", W.lk_s.p, n, L, n, st);
         commit(C, pk, W, 1, W.lk_a.p, B * L, 0, 0, W.aff.p, st);
         commit(C, pk, W, 1, W.lk_s.p, B * L, 0, 0, W.aff.p + B * L, st);
-        int err = 0;
-        ZK_CUDA(cudaMemcpyAsync(&err, W.d_error.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        // A witness whose lookup input is missing from its table has no permuted pair: halo2 returns
+        // Error::ConstraintSystemFailure for that proof.  The flag is per proof: the others of the sub-batch are unaffected
+        // (the failed one keeps moving through the pipeline on whatever the kernel wrote; its output is zeroed at the end).
+        std::vector<int> err(B, 0);
+        ZK_CUDA(cudaMemcpyAsync(err.data(), W.d_error.p, B * sizeof(int), cudaMemcpyDeviceToHost, st));
         const g1_affine_t* pts = fetch_points(2 * B * L);
-        ZK_REQUIRE(err == 0, "create_proof: a lookup input is not in its table (ConstraintSystemFailure)");
+        for (size_t b = 0; b < B; ++b) if (err[b]) status[b] = PROOF_LOOKUP_FAILED;
         for (size_t b = 0; b < B; ++b)
             for (size_t l = 0; l < L; ++l) { ps[b].tr.write_point(pts[b * L + l]); ps[b].tr.write_point(pts[B * L + b * L + l]); }
     }
@@ -974,19 +1053,27 @@ static void prove_sub_batch(Context& C, PkEntry& pk, ProverWs& W, const fr_t* ad
             ZK_REQUIRE((size_t)(ps[b].tr.out - (proofs + b * pk.proof_len)) == pk.proof_len, "internal: proof length mismatch");
         }
     }
+    // failed proofs: no bytes, only a status (the reference fails that request alone, tee/.../server.rs:189-190)
+    for (size_t b = 0; b < B; ++b) {
+        if (status[b] != PROOF_OK) memset(proofs + b * pk.proof_len, 0, pk.proof_len);
+        if (V.status) V.status[b] = status[b];
+    }
     timer.lap(6);
 }
 
-static void prove_batch(uint64_t handle, const uint64_t* advice, bool advice_on_device, const uint64_t* instance, size_t num_pi, size_t m,
-                        const uint64_t* seeds, uint8_t* proofs, size_t proof_len) {
-    Context& C = ctx(); C.require();
-    auto it = g_pks.find(handle);
-    ZK_REQUIRE(it != g_pks.end(), "unknown proving key handle");
-    PkEntry& pk = *it->second;
-    ZK_REQUIRE(proof_len == pk.proof_len, "prove: proof_len does not match the circuit (see zkgpu_pk_info)");
-    ZK_REQUIRE(m == 0 || (advice && seeds && proofs), "null pointer");
-    ZK_REQUIRE(num_pi == 0 || instance, "null pointer");
-    ZK_REQUIRE(num_pi <= pk.ustart, "prove: InstanceTooLarge");
+// ---------------------------------------------------------------------------------------------
+// zkgpu_prove_batch on ONE device: pipeline workers over sub-batches
+// ---------------------------------------------------------------------------------------------
+struct BatchArgs {
+    const fr_t* advice; bool advice_on_device;
+    const fr_t* instance; size_t num_pi; size_t m;
+    const RngRef* rng; uint8_t* proofs; int32_t* status;
+};
+static void prove_batch_on_device(PkEntry& pk, const BatchArgs& a) {
+    Context& C = *pk.C;
+    C.bind();
+    std::lock_guard<std::mutex> lk(pk.batch_mu);
+    const size_t m = a.m;
     size_t Bmax = default_batch(pk);
     // Pipeline workers (host thread + stream + workspace each) take alternate sub-batches, so one worker's
     // transcript hashing and bookkeeping overlap the other's kernels.  Kernel-class timing and stage tracing
@@ -995,46 +1082,152 @@ static void prove_batch(uint64_t handle, const uint64_t* advice, bool advice_on_
     // Three workers from six sub-batches on (measured 646 -> 655 proofs/s: the digit sort and the other kernels that do not live on
     // the IMAD pipe find more IMAD-bound work of other streams to overlap with), two from two on.
     unsigned workers = (g_ktime_on || g_trace) ? 1 : nsub >= 6 ? 3 : nsub >= 2 ? 2 : 1;
-    if (const char* e = getenv("ZKGPU_PROVER_WORKERS")) { int v = atoi(e); if (v >= 1 && v <= 3 && (unsigned)v < workers) workers = (unsigned)v; }
+    if (const char* e = getenv("ZKGPU_PROVER_WORKERS")) { int v = atoi(e); if (v >= 1 && v <= (int)BATCH_WORKERS && (unsigned)v < workers) workers = (unsigned)v; }
     if (workers >= 2 && Bmax > 1) { Bmax = std::max<size_t>(1, std::min(Bmax, (m + 2 * workers - 1) / (2 * workers))); nsub = (m + Bmax - 1) / Bmax; }
-    const fr_t* adv = reinterpret_cast<const fr_t*>(advice);
-    const fr_t* inst = reinterpret_cast<const fr_t*>(instance);
     // sub-batches as (offset, count).  With host advice the very first one is a quarter of the usual size: nothing can hide its
     // upload, so the GPU should start on a short one while the other worker's full-size upload is still in flight.
     std::vector<std::pair<size_t, size_t>> segs;
     {
         size_t off = 0;
-        if (workers >= 2 && !advice_on_device && m > Bmax && Bmax >= 8) { segs.push_back({0, Bmax / 4}); off = Bmax / 4; }
+        if (workers >= 2 && !a.advice_on_device && m > Bmax && Bmax >= 8) { segs.push_back({0, Bmax / 4}); off = Bmax / 4; }
         while (off < m) { size_t B = std::min(Bmax, m - off); segs.push_back({off, B}); off += B; }
     }
+    const size_t adv_per = (size_t)pk.A * pk.n;
     auto run = [&](unsigned w) {
-        ZK_CUDA(cudaSetDevice(C.device));
+        C.bind();
         pk.ws[w].prefetched_src = nullptr;
         for (size_t i = w; i < segs.size(); i += workers) {
-            const size_t off = segs[i].first, B = segs[i].second;
+            const size_t off = segs[i].first;
             const bool has_next = i + workers < segs.size();
-            const fr_t* next = has_next ? adv + segs[i + workers].first * pk.A * pk.n : nullptr;
-            prove_sub_batch(C, pk, pk.ws[w], adv + off * pk.A * pk.n, advice_on_device, inst + off * num_pi, num_pi, B, seeds + off,
-                            proofs + off * proof_len, next, has_next ? segs[i + workers].second : 0);
+            BatchView V;
+            V.B = segs[i].second; V.num_pi = a.num_pi;
+            V.advice = a.advice + off * adv_per; V.advice_on_device = a.advice_on_device;
+            V.instance = a.instance + off * a.num_pi; V.rng = a.rng + off;
+            V.proofs = a.proofs + off * pk.proof_len; V.status = a.status ? a.status + off : nullptr;
+            V.next_advice = has_next ? a.advice + segs[i + workers].first * adv_per : nullptr;
+            V.next_B = has_next ? segs[i + workers].second : 0;
+            prove_sub_batch(pk, pk.ws[w], V);
         }
     };
     if (workers == 1) { run(0); return; }
-    std::exception_ptr err[3];
-    std::thread th[3];
+    std::exception_ptr err[BATCH_WORKERS];
+    std::thread th[BATCH_WORKERS];
     for (unsigned w = 0; w < workers; ++w) th[w] = std::thread([&, w] { try { run(w); } catch (...) { err[w] = std::current_exception(); } });
     for (unsigned w = 0; w < workers; ++w) th[w].join();
     for (auto& e : err) if (e) std::rethrow_exception(e);
 }
 
+// ---------------------------------------------------------------------------------------------
+// zkgpu_prove_batch: shard the batch over the selected devices (replicas of the key material, contiguous
+// shards of the proofs, one host thread per GPU, no collective)
+// ---------------------------------------------------------------------------------------------
+static void check_batch_args(const PkEntry& pk, const void* advice, const void* instance, size_t num_pi, size_t m, const void* rng,
+                             const void* proofs, size_t proof_len, int rng_mode) {
+    ZK_REQUIRE(proof_len == pk.proof_len, "prove: proof_len does not match the circuit (see zkgpu_pk_info)");
+    ZK_REQUIRE(m == 0 || (advice && rng && proofs), "null pointer");
+    ZK_REQUIRE(num_pi == 0 || instance, "null pointer");
+    ZK_REQUIRE(num_pi <= pk.ustart, "prove: InstanceTooLarge");
+    ZK_REQUIRE(rng_mode == RNG_SEED_U64 || rng_mode == RNG_XOSHIRO_STATE || rng_mode == RNG_CHACHA20_SEED, "prove: unknown rng_mode");
+}
+
+static void prove_batch(uint64_t handle, const uint64_t* advice, bool advice_on_device, const uint64_t* instance, size_t num_pi, size_t m,
+                        int rng_mode, void* rng_data, uint8_t* proofs, size_t proof_len, int32_t* status) {
+    Runtime& R = rt(); R.require();
+    std::shared_ptr<PkShared> P = find_pk(handle);
+    check_batch_args(*P->dev[0], advice, instance, num_pi, m, rng_data, proofs, proof_len, rng_mode);
+    if (m == 0) return;
+    std::vector<RngRef> rng(m);
+    const size_t stride = rng_data_stride(rng_mode);
+    for (size_t i = 0; i < m; ++i) { rng[i].mode = rng_mode; rng[i].data = static_cast<uint8_t*>(rng_data) + i * stride; }
+    BatchArgs all{reinterpret_cast<const fr_t*>(advice), advice_on_device, reinterpret_cast<const fr_t*>(instance), num_pi, m, rng.data(), proofs, status};
+    if (advice_on_device) {   // resident advice: the device that holds it proves the whole batch
+        Context& C = R.of_pointer(advice);
+        prove_batch_on_device(*P->dev[C.slot], all);
+        return;
+    }
+    const size_t G = std::min<size_t>(P->dev.size(), m);
+    if (G == 1) { prove_batch_on_device(*P->dev[0], all); return; }
+    std::vector<std::thread> th(G);
+    std::vector<std::exception_ptr> err(G);
+    const size_t adv_per = (size_t)P->dev[0]->A * P->dev[0]->n;
+    for (size_t g = 0; g < G; ++g) {
+        const size_t lo = m * g / G, hi = m * (g + 1) / G;
+        BatchArgs a = all;
+        a.advice = all.advice + lo * adv_per; a.instance = all.instance + lo * num_pi; a.m = hi - lo; a.rng = all.rng + lo;
+        a.proofs = proofs + lo * proof_len; a.status = status ? status + lo : nullptr;
+        th[g] = std::thread([&, g, a] { try { prove_batch_on_device(*P->dev[g], a); } catch (...) { err[g] = std::current_exception(); } });
+    }
+    for (auto& t : th) t.join();
+    for (auto& e : err) if (e) std::rethrow_exception(e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// zkgpu_prove: blocking single-proof call, coalesced
+// ---------------------------------------------------------------------------------------------
+static size_t coalesce_cap(const PkEntry& pk) {
+    static const size_t env = [] { const char* e = getenv("ZKGPU_COALESCE_MAX"); long v = e ? atol(e) : 0; return v > 0 ? (size_t)v : (size_t)0; }();
+    return std::max<size_t>(1, std::min(env ? env : (size_t)64, default_batch(pk)));
+}
+static void dispatcher_loop(PkShared* P, unsigned dev_slot, unsigned worker) {
+    PkEntry& pk = *P->dev[dev_slot];
+    Coalescer& co = P->co;
+    ProverWs& W = pk.ws[BATCH_WORKERS + worker];
+    try { pk.C->bind(); } catch (...) {}
+    const size_t cap = coalesce_cap(pk);
+    std::unique_lock<std::mutex> lk(co.mu);
+    for (;;) {
+        ++co.idle;
+        co.cv_work.wait(lk, [&] { return co.stop || !co.q.empty(); });
+        if (co.stop && co.q.empty()) { --co.idle; return; }
+        // Take a fair share of what is waiting: with several idle dispatchers the queue is split between them, so their
+        // sub-batches run concurrently (one's transcript hashing overlaps the other's kernels) instead of one after the other.
+        const size_t share = (co.q.size() + co.idle - 1) / std::max(1u, co.idle);
+        --co.idle;
+        std::vector<ProveReq*> reqs;
+        const size_t num_pi = co.q.front()->num_pi;
+        while (!co.q.empty() && reqs.size() < std::min(cap, std::max<size_t>(1, share)) && co.q.front()->num_pi == num_pi) {
+            reqs.push_back(co.q.front()); co.q.pop_front();
+        }
+        co.batches++; co.requests += reqs.size(); co.max_batch_seen = std::max<uint64_t>(co.max_batch_seen, reqs.size());
+        lk.unlock();
+        const size_t B = reqs.size();
+        int rc = ZKGPU_OK; std::string msg;
+        std::vector<int32_t> status(B, 0);
+        try {
+            std::vector<const fr_t*> adv(B);
+            std::vector<fr_t> inst(B * num_pi);
+            std::vector<RngRef> rng(B);
+            std::vector<uint8_t> proofs(B * pk.proof_len);
+            for (size_t b = 0; b < B; ++b) {
+                adv[b] = reqs[b]->advice;
+                if (num_pi) memcpy(&inst[b * num_pi], reqs[b]->instance, num_pi * sizeof(fr_t));
+                rng[b].mode = reqs[b]->rng_mode; rng[b].data = reqs[b]->rng_data;
+            }
+            BatchView V;
+            V.B = B; V.num_pi = num_pi; V.advice_ptrs = adv.data(); V.instance = inst.data(); V.rng = rng.data();
+            V.proofs = proofs.data(); V.status = status.data();
+            prove_sub_batch(pk, W, V);
+            for (size_t b = 0; b < B; ++b) memcpy(reqs[b]->proof_out, &proofs[b * pk.proof_len], pk.proof_len);
+        } catch (const zk::Error& e) { rc = e.code; msg = e.what(); }
+        catch (const std::exception& e) { rc = ZKGPU_ERR_INTERNAL; msg = e.what(); }
+        lk.lock();
+        for (size_t b = 0; b < B; ++b) { reqs[b]->rc = rc; reqs[b]->err = msg; reqs[b]->status = status[b]; reqs[b]->done = true; }
+        co.cv_done.notify_all();
+    }
+}
+static void start_dispatchers(PkShared* P) {
+    for (unsigned d = 0; d < P->dev.size(); ++d)
+        for (unsigned w = 0; w < COALESCE_WORKERS; ++w) P->co.threads.emplace_back(dispatcher_loop, P, d, w);
+}
+PkShared::~PkShared() {
+    { std::lock_guard<std::mutex> lk(co.mu); co.stop = true; }
+    co.cv_work.notify_all();
+    for (auto& t : co.threads) if (t.joinable()) t.join();
+}
+
 }  // namespace zk
 
 using namespace zk;
-
-#define API_BEGIN try { std::lock_guard<std::recursive_mutex> lk_(ctx().mu);
-#define API_END                                                           \
-    return ZKGPU_OK; }                                                    \
-    catch (const zk::Error& e) { g_last_error = e.what(); return e.code; } \
-    catch (const std::exception& e) { g_last_error = e.what(); return ZKGPU_ERR_INTERNAL; }
 
 extern "C" {
 
@@ -1044,56 +1237,135 @@ void zkgpu_prover_step_seconds(double out[8], int reset) {
 }
 void zkgpu_set_trace(void (*fn)(const char*, const void*, size_t)) { g_trace = fn; }
 int zkgpu_set_rayon_threads(unsigned num_threads) {
-    API_BEGIN
+    API_TRY
     ZK_REQUIRE(num_threads >= 1 && num_threads <= 65536, "rayon thread count out of range");
     g_rayon_threads.store(num_threads);
     API_END
 }
 
 int zkgpu_pk_create(uint64_t srs, const uint8_t* circuit_blob, size_t blob_len, uint64_t* pk_out) {
-    API_BEGIN
-    Context& C = ctx(); C.require();
+    API_TRY
     ZK_REQUIRE(circuit_blob && pk_out, "null pointer");
-    std::unique_ptr<PkEntry> pk = keygen(C, srs, circuit_blob, blob_len);
+    Runtime& R = rt(); R.require();
+    std::shared_ptr<PkShared> P(new PkShared);
+    const size_t G = R.devs.size();
+    P->dev.resize(G);
+    // keygen on every selected device (replicas of the proving key), one host thread each
+    std::vector<std::exception_ptr> err(G);
+    auto one = [&](size_t g) {
+        try {
+            DeviceScope scope(*R.devs[g]);
+            P->dev[g] = keygen(*R.devs[g], srs, circuit_blob, blob_len);
+        } catch (...) { err[g] = std::current_exception(); }
+    };
+    if (G == 1) one(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < G; ++g) th.emplace_back(one, g);
+        for (auto& t : th) t.join();
+    }
+    for (auto& e : err) if (e) std::rethrow_exception(e);
+    std::unique_lock<std::shared_mutex> tl(R.tab_mu);
     uint64_t h = g_next_pk++;
-    g_pks[h] = std::move(pk);
+    g_pks[h] = std::move(P);
     *pk_out = h;
     API_END
 }
 int zkgpu_pk_release(uint64_t pk) {
-    API_BEGIN
-    ZK_REQUIRE(g_pks.erase(pk) == 1, "unknown proving key handle");
+    API_TRY
+    std::shared_ptr<PkShared> P;
+    {
+        std::unique_lock<std::shared_mutex> tl(rt().tab_mu);
+        auto it = g_pks.find(pk);
+        ZK_REQUIRE(it != g_pks.end(), "unknown proving key handle");
+        P = it->second;
+        g_pks.erase(it);
+    }
+    P.reset();   // the last user (a call still in flight keeps its own reference) frees the device memory
     API_END
 }
 int zkgpu_pk_info(uint64_t pk, uint64_t info[16]) {
-    API_BEGIN
-    auto it = g_pks.find(pk);
-    ZK_REQUIRE(it != g_pks.end() && info, "unknown proving key handle");
-    const PkEntry& p = *it->second;
-    uint64_t v[16] = {p.k, p.n, p.A, p.F, p.cs.degree(), p.bf, p.P, p.Q, p.num_evals, p.proof_len, p.ek, p.S, p.plan.sets.size(), default_batch(p), 0, 0};
+    API_TRY
+    ZK_REQUIRE(info, "null pointer");
+    std::shared_ptr<PkShared> P = find_pk(pk);
+    const PkEntry& p = *P->dev[0];
+    p.C->bind();
+    uint64_t v[16] = {p.k, p.n, p.A, p.F, p.cs.degree(), p.bf, p.P, p.Q, p.num_evals, p.proof_len, p.ek, p.S, p.plan.sets.size(), default_batch(p),
+                      P->dev.size(), 0};
     memcpy(info, v, sizeof v);
     API_END
 }
 int zkgpu_pk_vk(uint64_t pk, uint64_t* fixed_commitments, uint64_t* perm_commitments, uint64_t digest[4]) {
-    API_BEGIN
-    auto it = g_pks.find(pk);
-    ZK_REQUIRE(it != g_pks.end(), "unknown proving key handle");
-    const PkEntry& p = *it->second;
+    API_TRY
+    std::shared_ptr<PkShared> P = find_pk(pk);
+    const PkEntry& p = *P->dev[0];
     if (fixed_commitments && !p.fixed_commitments.empty()) memcpy(fixed_commitments, p.fixed_commitments.data(), p.fixed_commitments.size() * 64);
     if (perm_commitments && !p.perm_commitments.empty()) memcpy(perm_commitments, p.perm_commitments.data(), p.perm_commitments.size() * 64);
     if (digest) memcpy(digest, p.digest.l, 32);
     API_END
 }
+int zkgpu_prove_batch_rng(uint64_t pk, const uint64_t* advice, const uint64_t* instance, size_t num_instance, size_t m,
+                          int rng_mode, void* rng_data, uint8_t* proofs_out, size_t proof_len, int32_t* status_out) {
+    API_TRY
+    prove_batch(pk, advice, false, instance, num_instance, m, rng_mode, rng_data, proofs_out, proof_len, status_out);
+    API_END
+}
+int zkgpu_prove_batch_rng_dev(uint64_t pk, const void* d_advice, const uint64_t* instance, size_t num_instance, size_t m,
+                              int rng_mode, void* rng_data, uint8_t* proofs_out, size_t proof_len, int32_t* status_out) {
+    API_TRY
+    prove_batch(pk, reinterpret_cast<const uint64_t*>(d_advice), true, instance, num_instance, m, rng_mode, rng_data, proofs_out, proof_len, status_out);
+    API_END
+}
+// Test / parity form: fresh `SmallRng::seed_from_u64` per proof, all-or-nothing result
+static int prove_batch_seeded(uint64_t pk, const uint64_t* advice, bool on_device, const uint64_t* instance, size_t num_instance, size_t m,
+                              const uint64_t* rng_seeds, uint8_t* proofs_out, size_t proof_len) {
+    API_TRY
+    std::vector<int32_t> status(m, 0);
+    prove_batch(pk, advice, on_device, instance, num_instance, m, RNG_SEED_U64, const_cast<uint64_t*>(rng_seeds), proofs_out, proof_len, status.data());
+    for (size_t i = 0; i < m; ++i)
+        if (status[i] == PROOF_LOOKUP_FAILED)
+            throw Error(ZK_ERR_ARG, "create_proof: a lookup input is not in its table (ConstraintSystemFailure) in proof " + std::to_string(i) +
+                                        "; the other proofs of the batch are valid (zkgpu_prove_batch_rng reports a status per proof)");
+    API_END
+}
 int zkgpu_prove_batch(uint64_t pk, const uint64_t* advice, const uint64_t* instance, size_t num_instance, size_t m,
                       const uint64_t* rng_seeds, uint8_t* proofs_out, size_t proof_len) {
-    API_BEGIN
-    prove_batch(pk, advice, false, instance, num_instance, m, rng_seeds, proofs_out, proof_len);
-    API_END
+    return prove_batch_seeded(pk, advice, false, instance, num_instance, m, rng_seeds, proofs_out, proof_len);
 }
 int zkgpu_prove_batch_dev(uint64_t pk, const void* d_advice, const uint64_t* instance, size_t num_instance, size_t m,
                           const uint64_t* rng_seeds, uint8_t* proofs_out, size_t proof_len) {
-    API_BEGIN
-    prove_batch(pk, reinterpret_cast<const uint64_t*>(d_advice), true, instance, num_instance, m, rng_seeds, proofs_out, proof_len);
+    return prove_batch_seeded(pk, reinterpret_cast<const uint64_t*>(d_advice), true, instance, num_instance, m, rng_seeds, proofs_out, proof_len);
+}
+
+int zkgpu_prove(uint64_t pk, const uint64_t* advice, const uint64_t* instance, size_t num_instance, int rng_mode, void* rng_data,
+                uint8_t* proof_out, size_t proof_len) {
+    API_TRY
+    rt().require();
+    std::shared_ptr<PkShared> P = find_pk(pk);
+    check_batch_args(*P->dev[0], advice, instance, num_instance, 1, rng_data, proof_out, proof_len, rng_mode);
+    std::call_once(P->co_once, start_dispatchers, P.get());
+    ProveReq req;
+    req.advice = reinterpret_cast<const fr_t*>(advice); req.instance = reinterpret_cast<const fr_t*>(instance); req.num_pi = num_instance;
+    req.rng_mode = rng_mode; req.rng_data = static_cast<uint8_t*>(rng_data); req.proof_out = proof_out;
+    Coalescer& co = P->co;
+    {
+        std::unique_lock<std::mutex> lk(co.mu);
+        ZK_REQUIRE(!co.stop, "proving key is being released");
+        co.q.push_back(&req);
+        co.cv_work.notify_all();
+        co.cv_done.wait(lk, [&] { return req.done; });
+    }
+    if (req.rc != ZKGPU_OK) throw Error(req.rc, req.err);
+    if (req.status == PROOF_LOOKUP_FAILED)
+        throw Error(ZKGPU_ERR_WITNESS, "create_proof: a lookup input is not in its table (ConstraintSystemFailure)");
+    API_END
+}
+int zkgpu_prove_stats(uint64_t pk, uint64_t out[4]) {
+    API_TRY
+    ZK_REQUIRE(out, "null pointer");
+    std::shared_ptr<PkShared> P = find_pk(pk);
+    std::lock_guard<std::mutex> lk(P->co.mu);
+    out[0] = P->co.requests; out[1] = P->co.batches; out[2] = P->co.max_batch_seen; out[3] = P->co.threads.size();
     API_END
 }
 

@@ -70,6 +70,7 @@ void launch_scatter_random(fr_t* dst, size_t proof_stride, size_t col_stride, si
                            size_t cols, size_t rows, cudaStream_t st) {
     size_t total = B * cols * rows;
     if (!total) return;
+    KtScope kt(KT_MISC, st);
     ZK_LAUNCH(k_scatter_random, ceil_div(total, 128), 128, 0, st, dst, proof_stride, col_stride, row_start, raw, B, cols, rows);
 }
 __global__ void k_reduce_wide(const uint64_t* raw, fr_t* out, size_t n) {
@@ -251,6 +252,7 @@ __global__ void k_chacha_poly(const uint8_t* seeds, fr_t* out, size_t n, size_t 
     fe_store(out + t, fr_from_wide(w));
 }
 void launch_chacha_poly(const uint8_t* seeds, fr_t* out, size_t n, size_t B, size_t chunk, size_t nchunks, cudaStream_t st) {
+    KtScope kt(KT_MISC, st);
     if (B * n) ZK_LAUNCH(k_chacha_poly, ceil_div(B * n, 128), 128, 0, st, seeds, out, n, B, chunk, nchunks);
 }
 
@@ -407,6 +409,7 @@ void launch_poly_eval(const EvalJob* jobs, fr_t* out, size_t num_jobs, unsigned 
     if (!num_jobs) return;
     size_t n = (size_t)1 << k;
     unsigned T = n >= ZK_EVAL_T ? ZK_EVAL_T : (unsigned)n;
+    KtScope kt(KT_POLY, st);
     ZK_LAUNCH(k_poly_eval, (unsigned)num_jobs, T, 0, st, jobs, out, k);
 }
 
@@ -424,6 +427,7 @@ __global__ void __launch_bounds__(128) k_lincomb(const LinTerm* terms, const uin
 void launch_lincomb(const LinTerm* terms, const uint32_t* job_off, fr_t* const* outs, size_t num_jobs, size_t n, cudaStream_t st) {
     if (!num_jobs) return;
     dim3 grid(ceil_div(n, 128), (unsigned)num_jobs);
+    KtScope kt(KT_POLY, st);
     ZK_LAUNCH(k_lincomb, grid, 128, 0, st, terms, job_off, outs, n);
 }
 __global__ void k_sub_low(fr_t* const* polys, const fr_t* low, size_t num_jobs) {
@@ -433,6 +437,7 @@ __global__ void k_sub_low(fr_t* const* polys, const fr_t* low, size_t num_jobs) 
     fe_store(polys[j] + i, fe_load(polys[j] + i) - fe_ldg(low + t));
 }
 void launch_sub_low(fr_t* const* polys, const fr_t* low, size_t num_jobs, cudaStream_t st) {
+    KtScope kt(KT_POLY, st);
     if (num_jobs) ZK_LAUNCH(k_sub_low, ceil_div(num_jobs * 4, 64), 64, 0, st, polys, low, num_jobs);
 }
 
@@ -491,6 +496,7 @@ void launch_kate_div(const DivJob* jobs, size_t num_jobs, unsigned k, cudaStream
     if (!num_jobs) return;
     size_t n = (size_t)1 << k;
     unsigned T = n >= ZK_DIV_T ? ZK_DIV_T : (unsigned)n;
+    KtScope kt(KT_POLY, st);
     ZK_LAUNCH(k_kate_div, (unsigned)num_jobs, T, 0, st, jobs, k);
 }
 

@@ -59,9 +59,10 @@ struct LookupCompressArgs {
 void launch_lookup_compress(const LookupCompressArgs& a, fr_t* out_in, fr_t* out_tab, size_t B, cudaStream_t st);
 // permute_expression_pair for B*L (input, table) pairs: sorts canonical values (rows < usable), assigns the table
 // column; perm_in / perm_tab [B*L][n] receive rows < usable (blinding rows are written separately).
-// sort_a / sort_t: scratch [B*L][n].  *d_error is set to 1 if an input value is missing from its table.
+// sort_a / sort_t: scratch [B*L][n].  d_error[b] (one flag per proof, b = pair / L) is set to 1 if an input value of
+// proof b is missing from its table.
 void launch_lookup_permute(const fr_t* comp_in, const fr_t* comp_tab, fr_t* perm_in, fr_t* perm_tab, fr_t* sort_a, fr_t* sort_t,
-                           unsigned k, size_t usable, size_t BL, int* d_error, cudaStream_t st);
+                           unsigned k, size_t usable, size_t BL, unsigned L, int* d_error, cudaStream_t st);
 // num = (in + beta)(tab + gamma), den = (perm_in + beta)(perm_tab + gamma); all [B][L][n]
 void launch_lookup_num_den(const fr_t* comp_in, const fr_t* comp_tab, const fr_t* perm_in, const fr_t* perm_tab, const Challenges* ch,
                            fr_t* num, fr_t* den, unsigned k, unsigned L, size_t B, cudaStream_t st);

@@ -54,8 +54,14 @@ def _u64(a):
     return np.ascontiguousarray(a, dtype=np.uint64)
 
 
-def init(device=0):
-    _chk(lib().zkgpu_init(int(device)))
+def init(device=0, mask=None):
+    """zkgpu_init(device_mask): `device` selects one CUDA device (mask 1 << device); `mask` selects several (bit i = device i,
+    0 = every visible device) for the single-process multi-GPU mode."""
+    _chk(lib().zkgpu_init(int(mask) if mask is not None else 1 << int(device)))
+
+
+def device_count():
+    return int(lib().zkgpu_device_count())
 
 
 def shutdown():
@@ -116,6 +122,22 @@ def params_setup(k, seed, lagrange=True):
     gl = np.empty((n, 8), dtype=np.uint64) if lagrange else None
     _chk(lib().zkgpu_params_setup(C.c_uint32(k), C.c_uint64(seed), _p(g), _p(gl) if lagrange else None))
     return g, gl
+
+
+def params_setup_rng(k, rng_state):
+    """ParamsKZG::setup(k, &mut rng) with a running SmallRng: rng_state (4,) uint64 is advanced in place"""
+    n = 1 << k
+    g = np.empty((n, 8), dtype=np.uint64)
+    gl = np.empty((n, 8), dtype=np.uint64)
+    _chk(lib().zkgpu_params_setup_rng(C.c_uint32(k), _p(rng_state), _p(g), _p(gl)))
+    return g, gl
+
+
+def fr_random_rng(rng_state, n):
+    """n x Fr::random(&mut rng) from a running SmallRng (state advanced in place)"""
+    out = np.empty((n, 4), dtype=np.uint64)
+    _chk(lib().zkgpu_fr_random_rng(_p(rng_state), _p(out), C.c_size_t(n)))
+    return out
 
 
 def g1_sum(points):
@@ -225,7 +247,7 @@ class ProvingKey:
     (/root/reference/crates/shielder_bindings/src/circuits/mod.rs:103-111)."""
 
     INFO = ("k", "n", "num_advice", "num_fixed", "degree", "blinding_factors", "num_perm_sets", "num_quotients",
-            "num_evals", "proof_len", "extended_k", "num_perm_columns", "num_rotation_sets", "sub_batch")
+            "num_evals", "proof_len", "extended_k", "num_perm_columns", "num_rotation_sets", "sub_batch", "replicas")
 
     def __init__(self, params, circuit_blob):
         self.params = params
@@ -258,6 +280,39 @@ class ProvingKey:
                                      _p(seeds), _p(out), C.c_size_t(self.proof_len)))
         raw = out.tobytes()
         return [raw[i * self.proof_len:(i + 1) * self.proof_len] for i in range(m)]
+
+    RNG_SEED_U64, RNG_XOSHIRO_STATE, RNG_CHACHA20_SEED = 0, 1, 2
+    PROOF_OK, PROOF_LOOKUP_FAILED = 0, 1
+
+    def prove_batch_rng(self, advice, instance, rng_mode, rng_data):
+        """zkgpu_prove_batch_rng: rng_data is a C-contiguous numpy array — (m,) uint64 seeds, (m, 4) uint64 running SmallRng
+        states (advanced IN PLACE) or (m, 32) uint8 ChaCha20 seeds.  Returns (proofs, status): a failed proof is b"" """
+        advice, instance = _u64(advice), _u64(instance)
+        m = {0: rng_data.size, 1: rng_data.size // 4, 2: rng_data.size // 32}[rng_mode]
+        if advice.size != m * self.num_advice * self.n * 4:
+            raise ZkGpuError("prove_batch: advice must be m x num_advice x n field elements")
+        if not rng_data.flags["C_CONTIGUOUS"]:
+            raise ZkGpuError("rng_data must be C-contiguous (it is updated in place)")
+        num_pi = instance.size // (4 * m) if m else 0
+        out = np.zeros(m * self.proof_len, dtype=np.uint8)
+        status = np.zeros(m, dtype=np.int32)
+        _chk(lib().zkgpu_prove_batch_rng(C.c_uint64(self.handle), _p(advice), _p(instance), C.c_size_t(num_pi), C.c_size_t(m),
+                                         int(rng_mode), _p(rng_data), _p(out), C.c_size_t(self.proof_len), _p(status)))
+        raw = out.tobytes()
+        return [raw[i * self.proof_len:(i + 1) * self.proof_len] if status[i] == 0 else b"" for i in range(m)], status
+
+    def prove_one(self, advice, instance, rng_mode, rng_data):
+        """zkgpu_prove: one blocking proof; concurrent callers (threads) are coalesced into batches by the library"""
+        advice, instance = _u64(advice), _u64(instance)
+        out = np.zeros(self.proof_len, dtype=np.uint8)
+        _chk(lib().zkgpu_prove(C.c_uint64(self.handle), _p(advice), _p(instance), C.c_size_t(instance.size // 4), int(rng_mode),
+                               _p(rng_data), _p(out), C.c_size_t(self.proof_len)))
+        return out.tobytes()
+
+    def prove_stats(self):
+        out = np.zeros(4, dtype=np.uint64)
+        _chk(lib().zkgpu_prove_stats(C.c_uint64(self.handle), _p(out)))
+        return dict(requests=int(out[0]), batches=int(out[1]), max_batch=int(out[2]), dispatchers=int(out[3]))
 
     def prove_batch_dev(self, d_advice_ptr, instance, seeds, out=None):
         """advice already resident in HBM (device pointer); returns the proofs as one uint8 array"""
