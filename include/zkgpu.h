@@ -61,6 +61,16 @@ int zkgpu_abi_version(void);
 /* ---- MSM: halo2curves::msm::best_multiexp(coeffs, bases) -> G1 -------------------------------- */
 int zkgpu_msm_g1(const uint64_t* scalars, const uint64_t* bases_affine, size_t n, uint64_t out_jacobian[12]);
 
+/* ---- best_multiexp with RESIDENT bases, points split across the selected devices ("partition points into G
+ * contiguous shards; each GPU runs a full Pippenger on its shard -> one point; gather G points over NVLink P2P, G - 1 EC adds").
+ * zkgpu_bases_register uploads shard g of the n points to device g only.  zkgpu_msm_g1_bases(handle, scalars, n, out, kernel_ms):
+ * scalars = n field elements in host memory, or NULL to reuse the scalars the previous call left in HBM (kernel-only timing);
+ * kernel_ms (may be NULL) receives the slowest shard's device time.  In the one-process-per-GPU deployment every rank registers its
+ * own shard and the 64-byte partial results are combined with zkgpu_g1_sum_affine. */
+int zkgpu_bases_register(const uint64_t* bases_affine, size_t n, uint64_t* handle_out);
+int zkgpu_bases_release(uint64_t bases);
+int zkgpu_msm_g1_bases(uint64_t bases, const uint64_t* scalars, size_t n, uint64_t out_jacobian[12], double* kernel_ms);
+
 /* ---- SRS-resident MSM: ParamsKZG::{commit, commit_lagrange} (poly/kzg/commitment.rs) -----------
  * zkgpu_srs_register uploads g and g_lagrange (n = 2^k points each, as ParamsKZG holds them;
  * crates/powers-of-tau/lib.rs:71 builds it, :280 `get_g`) once and precomputes the fixed-base window
@@ -98,6 +108,12 @@ int zkgpu_params_setup(uint32_t k, uint64_t seed, uint64_t* g_out, uint64_t* g_l
 int zkgpu_params_setup_rng(uint32_t k, uint64_t rng_state[4], uint64_t* g_out, uint64_t* g_lagrange_out);
 
 /* g_lagrange_out may be NULL (then k up to 24: bases for the large-MSM sweep). */
+/* g_out[i] = s^(start + i) * G, i < count: a slice of that setup's `g` (s = the first Fr::random of SmallRng::seed_from_u64(seed)),
+ * so one rank of a point-sharded MSM builds only its shard. */
+int zkgpu_setup_powers(uint64_t seed, uint64_t start, size_t count, uint64_t* g_out);
+
+/* halo2_proofs::arithmetic::eval_polynomial(poly, point): sum_i coeffs[i] * x^i. */
+int zkgpu_eval_polynomial(const uint64_t* coeffs, size_t n, const uint64_t x[4], uint64_t out[4]);
 
 /* Counts the points that are neither the identity (0,0) nor on y^2 = x^3 + 3: the `G1Affine::from_xy(..).unwrap()`
  * check of the ptau reader (/root/reference/crates/powers-of-tau/lib.rs:206-224). */

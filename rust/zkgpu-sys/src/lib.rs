@@ -32,6 +32,11 @@ extern "C" {
     pub fn zkgpu_params_setup(k: u32, seed: u64, g_out: *mut u64, g_lagrange_out: *mut u64) -> c_int;
     pub fn zkgpu_params_setup_rng(k: u32, rng_state: *mut u64, g_out: *mut u64, g_lagrange_out: *mut u64) -> c_int;
     pub fn zkgpu_fr_random_rng(rng_state: *mut u64, out: *mut u64, n: usize) -> c_int;
+    pub fn zkgpu_setup_powers(seed: u64, start: u64, count: usize, g_out: *mut u64) -> c_int;
+    pub fn zkgpu_eval_polynomial(coeffs: *const u64, n: usize, x: *const u64, out: *mut u64) -> c_int;
+    pub fn zkgpu_bases_register(bases_affine: *const u64, n: usize, handle_out: *mut u64) -> c_int;
+    pub fn zkgpu_bases_release(bases: u64) -> c_int;
+    pub fn zkgpu_msm_g1_bases(bases: u64, scalars: *const u64, n: usize, out_jacobian: *mut u64, kernel_ms: *mut f64) -> c_int;
     pub fn zkgpu_g1_sum_affine(points_affine: *const u64, n: usize, out_affine: *mut u64) -> c_int;
     pub fn zkgpu_g1_on_curve(points_affine: *const u64, n: usize, bad_count: *mut u64) -> c_int;
 

@@ -13,4 +13,11 @@ void emu_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint3
         else            { switch (op) { case 0: fq_mul(r, x, y); break; case 1: fq_add(r, x, y); break; case 2: fq_sub(r, x, y); break; default: fq_sqr(r, x); } }
     }
 }
+// out = a*b + c*d with one reduction (fe_mul_add2); carry-is-zero assertions of the dual product run inside
+void emu_mul_add2(int field, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        if (field == 0) fr_mul_add2(out + 8 * i, a + 8 * i, b + 8 * i, c + 8 * i, d + 8 * i);
+        else fq_mul_add2(out + 8 * i, a + 8 * i, b + 8 * i, c + 8 * i, d + 8 * i);
+    }
+}
 }

@@ -60,3 +60,19 @@ def test_limb_arithmetic_matches_oracle(emu, field, p):
         assert np.array_equal(run(emu, field, op, a, b), O.field_op(field, oop, a, b).reshape(-1, 4)), op
     assert np.array_equal(run(emu, field, 3, a), O.field_op(field, 4, a).reshape(-1, 4))
 
+
+
+@pytest.mark.parametrize("field,p", [(0, P.R_MOD), (1, P.Q_MOD)])
+def test_dual_product_with_one_reduction(emu, field, p):
+    """fe_mul_add2(a, b, c, d) = a*b + c*d (the Y-coordinate of every point addition): same value as two products and a modular
+    addition, on extreme operands (all four at p - 1 maximise every partial sum of the nine-limb frame) and random ones."""
+    rng = np.random.default_rng(17 + field)
+    edge = [0, 1, p - 1, p - 2, (1 << 253), (1 << 32) - 1, int("ffffffff" * 7, 16) % p, int("80000000" * 8, 16) % p, (p - 1) // 2]
+    quads = [(a, b, c, d) for a in edge for b in edge[:5] for c in edge[2:6] for d in edge]
+    quads += [tuple(int.from_bytes(rng.bytes(40), "little") % p for _ in range(4)) for _ in range(20000)]
+    cols = [P.int_to_limbs([q[i] for q in quads]) for i in range(4)]
+    u32 = [np.ascontiguousarray(c, dtype=np.uint64).view(np.uint32) for c in cols]
+    out = np.empty_like(u32[0])
+    emu.emu_mul_add2(field, *[x.ctypes.data_as(C.c_void_p) for x in u32], out.ctypes.data_as(C.c_void_p), C.c_size_t(len(quads)))
+    want = O.field_op(field, 1, O.field_op(field, 0, cols[0], cols[1]), O.field_op(field, 0, cols[2], cols[3])).reshape(-1, 4)
+    assert np.array_equal(out.view(np.uint64).reshape(-1, 4), want)

@@ -3,6 +3,8 @@ size-independent checks of the NTT sweep.  Above the sizes the CPU oracle finish
 value comes from a domain property instead: with the setup SRS g[i] = s^i * G,
     sum_i c_i * g[i] == [ p(s) ] * G ,   p(X) = sum_i c_i X^i
 so one Horner evaluation and one scalar multiplication on the CPU pin an MSM of any size bit-exactly."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -107,3 +109,39 @@ def test_prove_batch_empty(big_bases):
     pk = zkgpu.ProvingKey(params, circ.blob)
     assert pk.prove_batch(np.zeros((0, shape.num_advice, shape.n, 4), dtype=np.uint64), np.zeros((0, 3, 4), dtype=np.uint64), []) == []
     pk.release(); params.release()
+
+
+def test_eval_polynomial_matches_oracle():
+    """zkgpu_eval_polynomial = halo2 eval_polynomial: empty, length 1, ragged (non power of two), long"""
+    zkgpu.init(0)
+    x = GpuBackend.random(31, 1)[0]
+    assert not zkgpu.eval_polynomial(np.zeros((0, 4), dtype=np.uint64), x).any()
+    for n in (1, 2, 7, 1000, 8192, 70001, (1 << 18) + 3):
+        c = GpuBackend.random(32 + n % 7, n)
+        assert np.array_equal(zkgpu.eval_polynomial(c, x), O.eval_polynomial(c, x)), n
+
+
+def test_setup_powers_is_a_slice_of_the_setup_srs(big_bases):
+    g = big_bases(14)
+    assert np.array_equal(zkgpu.setup_powers(SEED, 0, 100), g[:100])
+    assert np.array_equal(zkgpu.setup_powers(SEED, 5000, 3000), g[5000:8000])
+
+
+@pytest.mark.parametrize("log_n", [11, 16, 20])
+def test_resident_bases_msm(big_bases, log_n):
+    """zkgpu_msm_g1_bases (bases resident, scalars streamed or resident) == best_multiexp == [p(s)] G"""
+    n = 1 << log_n
+    g = big_bases(log_n)
+    c = _scalars("uniform", n)
+    bases = zkgpu.Bases(g)
+    try:
+        want = _expected(c)
+        assert np.array_equal(bases.msm(c), want)
+        assert np.array_equal(bases.msm(None), want)          # scalars left resident by the previous call
+        assert bases.kernel_ms > 0
+        c2 = _scalars("sparse", n)
+        assert np.array_equal(bases.msm(c2), zkgpu.best_multiexp(c2, g))
+        with pytest.raises(zkgpu.ZkGpuError):
+            zkgpu._chk(zkgpu.lib().zkgpu_msm_g1_bases(C.c_uint64(bases.handle), zkgpu._p(c), C.c_size_t(n - 1), zkgpu._p(np.zeros(12, np.uint64)), None))
+    finally:
+        bases.release()

@@ -22,9 +22,9 @@ def _worker(rank, world, port, n, ret_dir):
     raw = O.srs_read(O.RAW11, 0)
     scalars = O.random_fr(5, n)
     bases = raw["g"][:n]
-    got = multi.msm_sharded(scalars, bases, dist, lambda c, b: O.msm(c, b))
-    want = O.msm(scalars, bases, threads=2)
     lo, hi = multi.shard_bounds(n, rank, world)
+    got = multi.msm_sharded(scalars[lo:hi], bases[lo:hi], dist, lambda c, b: O.msm(c, b))   # a rank is handed its shard only
+    want = O.msm(scalars, bases, threads=2)
     np.save(os.path.join(ret_dir, "r%d.npy" % rank), np.concatenate([got, want, np.array([lo, hi], dtype=np.uint64)]))
     dist.barrier()
     dist.destroy_process_group()

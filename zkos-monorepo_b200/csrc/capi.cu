@@ -8,6 +8,7 @@
 
 namespace zk {
 void prover_release_all();  // prover.cu
+void bases_release_all();   // msm_sharded.cu
 std::atomic<uint64_t> g_launches{0};
 Runtime& rt() { static Runtime r; return r; }
 Context& ctx() { Context& c = rt().primary(); c.bind(); return c; }
@@ -127,6 +128,7 @@ void Runtime::shutdown() {
     std::lock_guard<std::mutex> lk(init_mu);
     if (!inited) return;
     prover_release_all();
+    bases_release_all();
     {
         std::unique_lock<std::shared_mutex> tl(tab_mu);
         for (auto& d : devs) d->release_all();
@@ -446,6 +448,41 @@ int zkgpu_fr_random_rng(uint64_t rng_state[4], uint64_t* out, size_t n) {
     SmallRng rng(rng_state);
     fr_random_from(rng, out, n);
     memcpy(rng_state, rng.s, 32);
+    API_END
+}
+
+/* halo2_proofs::arithmetic::eval_polynomial(poly, point) (reference call site
+ * /root/reference/crates/powers-of-tau/lib.rs:151): Horner evaluation of n coefficients at x. */
+int zkgpu_eval_polynomial(const uint64_t* coeffs, size_t n, const uint64_t x[4], uint64_t out[4]) {
+    API_BEGIN
+    Context& C = ctx();
+    ZK_REQUIRE((coeffs || n == 0) && x && out, "null pointer");
+    fr_t xv; memcpy(xv.l, x, 32);
+    fr_t acc = fr_t::zero();
+    if (n) {
+        // chunks of 2^log_c coefficients (zero-padded at the top), one CTA each; the chunk values are folded on the host:
+        // p(x) = sum_j x^(j 2^log_c) p_j(x)
+        unsigned log_c = 0;
+        while (log_c < 16 && ((size_t)1 << log_c) < n) ++log_c;
+        const size_t chunk = (size_t)1 << log_c, jobs_n = (n + chunk - 1) / chunk;
+        cudaStream_t st = C.stream;
+        C.fr_buf.ensure(jobs_n * chunk + jobs_n);
+        fr_t* d_vals = C.fr_buf.p + jobs_n * chunk;
+        if (jobs_n * chunk > n) ZK_CUDA(cudaMemsetAsync(C.fr_buf.p + n, 0, (jobs_n * chunk - n) * sizeof(fr_t), st));
+        ZK_CUDA(cudaMemcpyAsync(C.fr_buf.p, coeffs, n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+        std::vector<EvalJob> jobs(jobs_n);
+        for (size_t j = 0; j < jobs_n; ++j) { jobs[j].poly = C.fr_buf.p + j * chunk; jobs[j].x = xv; }
+        DevBuf<EvalJob> d_jobs(jobs_n);
+        ZK_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs_n * sizeof(EvalJob), cudaMemcpyHostToDevice, st));
+        launch_poly_eval(d_jobs.p, d_vals, jobs_n, log_c, st);
+        std::vector<fr_t> vals(jobs_n);
+        ZK_CUDA(cudaMemcpyAsync(vals.data(), d_vals, jobs_n * sizeof(fr_t), cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(cudaStreamSynchronize(st));
+        fr_t xc = xv;
+        for (unsigned i = 0; i < log_c; ++i) xc = sqr(xc);
+        for (size_t j = jobs_n; j-- > 0;) acc = acc * xc + vals[j];
+    }
+    memcpy(out, acc.l, 32);
     API_END
 }
 

@@ -2,7 +2,8 @@
 //   affine  : (x, y) Montgomery, identity = (0,0)  — the halo2curves `G1Affine` memory layout
 //             (crates/powers-of-tau/lib.rs:190-231 reads this layout)
 //   XYZZ    : (X, Y, ZZ, ZZZ), x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2, identity has ZZ = 0.
-//             Used for bucket accumulation: mixed add 8M+2S, add 12M+2S, double 6M+3S.
+//             Used for bucket accumulation: mixed add 8M+2S, add 12M+2S, double 6M+3S; the two products of every
+//             Y3 = R (Q - X3) - Y1 PPP share one Montgomery reduction (fe_mul_add2).
 // Every exceptional case (identity operands, P+P, P-P) is handled, so results are exact group
 // elements regardless of accumulation order — required for bit-exact parity after normalisation.
 #pragma once
@@ -38,7 +39,7 @@ __host__ __device__ inline g1_xyzz_t xyzz_dbl(const g1_xyzz_t& p) {
     fq_t X2 = sqr(p.x), M = dbl(X2) + X2;
     g1_xyzz_t r;
     r.x = sqr(M) - dbl(S);
-    r.y = M * (S - r.x) - W * p.y;
+    r.y = fe_mul_add2(M, S - r.x, neg(W), p.y);
     r.zz = V * p.zz;
     r.zzz = W * p.zzz;
     return r;
@@ -50,7 +51,7 @@ __host__ __device__ inline g1_xyzz_t xyzz_dbl_affine(const g1_affine_t& p) {
     fq_t X2 = sqr(p.x), M = dbl(X2) + X2;
     g1_xyzz_t r;
     r.x = sqr(M) - dbl(S);
-    r.y = M * (S - r.x) - W * p.y;
+    r.y = fe_mul_add2(M, S - r.x, neg(W), p.y);
     r.zz = V;
     r.zzz = W;
     return r;
@@ -72,7 +73,7 @@ __host__ __device__ inline void xyzz_madd(g1_xyzz_t& acc, const g1_affine_t& q, 
     }
     fq_t PP = sqr(P), PPP = P * PP, Q = acc.x * PP;
     fq_t X3 = sqr(R) - PPP - dbl(Q);
-    acc.y = R * (Q - X3) - acc.y * PPP;
+    acc.y = fe_mul_add2(R, Q - X3, neg(acc.y), PPP);   // R (Q - X3) - Y1 PPP, one reduction
     acc.x = X3;
     acc.zz = acc.zz * PP;
     acc.zzz = acc.zzz * PPP;
@@ -90,7 +91,7 @@ __host__ __device__ inline g1_xyzz_t xyzz_add(const g1_xyzz_t& a, const g1_xyzz_
     fq_t PP = sqr(P), PPP = P * PP, Q = U1 * PP;
     g1_xyzz_t r;
     r.x = sqr(R) - PPP - dbl(Q);
-    r.y = R * (Q - r.x) - S1 * PPP;
+    r.y = fe_mul_add2(R, Q - r.x, neg(S1), PPP);
     r.zz = a.zz * b.zz * PP;
     r.zzz = a.zzz * b.zzz * PPP;
     return r;

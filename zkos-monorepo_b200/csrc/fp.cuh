@@ -47,6 +47,10 @@ __host__ __device__ __forceinline__ fq_t operator+(const fq_t& a, const fq_t& b)
 __host__ __device__ __forceinline__ fq_t operator-(const fq_t& a, const fq_t& b) { fq_t r; fq_sub(r.l, a.l, b.l); return r; }
 __host__ __device__ __forceinline__ fq_t sqr(const fq_t& a) { fq_t r; fq_sqr(r.l, a.l); return r; }
 
+// a*b + c*d with ONE Montgomery reduction (gen_fp.py `dual`): 192 wide multiplies instead of 2 x 128, and no modular addition
+__host__ __device__ __forceinline__ fr_t fe_mul_add2(const fr_t& a, const fr_t& b, const fr_t& c, const fr_t& d) { fr_t r; fr_mul_add2(r.l, a.l, b.l, c.l, d.l); return r; }
+__host__ __device__ __forceinline__ fq_t fe_mul_add2(const fq_t& a, const fq_t& b, const fq_t& c, const fq_t& d) { fq_t r; fq_mul_add2(r.l, a.l, b.l, c.l, d.l); return r; }
+
 __host__ __device__ __forceinline__ void fe_set_one(fr_t& r) { fr_set_one(r.l); }
 __host__ __device__ __forceinline__ void fe_set_one(fq_t& r) { fq_set_one(r.l); }
 __host__ __device__ __forceinline__ void fe_set_r2(fr_t& r) { fr_set_r2(r.l); }

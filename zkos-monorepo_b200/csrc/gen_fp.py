@@ -120,8 +120,14 @@ def emit_c_chain(chain, check_carry_free):
     return "\n".join(out)
 
 
-def gen_mont_mul(mod, sqr=False, tri=False):
+def gen_mont_mul(mod, sqr=False, tri=False, dual=False):
     """Returns list of (chain, carry_must_be_zero) computing r = a*b/2^256 mod p into r[0..7].
+
+    dual: r = (a*b + c*d)/2^256 mod p with ONE interleaved reduction — step i accumulates a*b_i and c*d_i before m_i is
+    formed, so the second product costs its 64 wide multiplies but no second reduction (64 + 8 multiplies, a conditional
+    subtraction and the modular addition of the two results are saved).  Bounds: every partial sum is below
+    2^32 (3p + 1) < 2^288, i.e. fits the nine-limb frame of the even/odd accumulators (the emulation asserts the top
+    carries), and the result (ab + cd + m p)/2^256 < p (2p/2^256 + 1) < 2p needs one conditional subtraction.
 
     tri (squaring only): triangular product.  a^2 = sum_i a_i 2^(32 i) * (a_i 2^(32 i) + sum_{j>i} 2 a_j 2^(32 j)), so step i
     multiplies a_i by the limbs j >= i of (a_i, 2a) only: 36 wide products instead of 64.  d = 2a is one carry chain of eight
@@ -134,6 +140,9 @@ def gen_mont_mul(mod, sqr=False, tri=False):
     flags = []
     A = ["a[%d]" % i for i in range(N)]
     Bv = ["b[%d]" % i for i in range(N)] if not sqr else A
+    Cv = ["c[%d]" % i for i in range(N)]
+    Dv = ["d[%d]" % i for i in range(N)]
+    assert not (dual and sqr)
     ev = ["ev[%d]" % i for i in range(N)]
     od = ["od[%d]" % i for i in range(N)]
     tri = tri and sqr
@@ -192,6 +201,22 @@ def gen_mont_mul(mod, sqr=False, tri=False):
                     mad("madc.lo.cc", e[j], X(j), bi, e[j])
                     mad("madc.hi.cc", e[j + 1], X(j), bi, e[j + 1])
                 p.ins("addc", o[N - 1], o[N - 1], 0)
+        if dual:
+            # second product of the step: c * d_i into the same frame (odd limbs, then even limbs + carry into the top)
+            di = Dv[i]
+            p.chain(); flags.append(True)
+            p.ins("mad.lo.cc", o[0], Cv[1], di, o[0])
+            p.ins("madc.hi.cc", o[1], Cv[1], di, o[1])
+            for j in range(2, N, 2):
+                p.ins("madc.lo.cc", o[j], Cv[j + 1], di, o[j])
+                p.ins("madc.hi.cc", o[j + 1], Cv[j + 1], di, o[j + 1])
+            p.chain(); flags.append(False)
+            p.ins("mad.lo.cc", e[0], Cv[0], di, e[0])
+            p.ins("madc.hi.cc", e[1], Cv[0], di, e[1])
+            for j in range(2, N, 2):
+                p.ins("madc.lo.cc", e[j], Cv[j], di, e[j])
+                p.ins("madc.hi.cc", e[j + 1], Cv[j], di, e[j + 1])
+            p.ins("addc", o[N - 1], o[N - 1], 0)
         p.chain(); flags.append(False)
         p.ins("mul.lo", "mi", e[0], m0)
         # odd += MOD[odd limbs] * mi   (top carry is provably zero; the emulation asserts it)
@@ -484,6 +509,18 @@ def emit_field(name, mod):
         o.append("#endif")
         o.append("    for (int i = 0; i < 8; ++i) r[i] = bw ? ev[i] : t[i];")
         o.append("}")
+    # r = a*b + c*d with one reduction
+    o.append("ZK_FP_FN void %s_mul_add2(uint32_t* __restrict__ r, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, "
+             "const uint32_t* __restrict__ c, const uint32_t* __restrict__ d) {" % name)
+    o.append("    uint32_t ev[8] = {0,0,0,0,0,0,0,0}, od[8] = {0,0,0,0,0,0,0,0}, t[8] = {0,0,0,0,0,0,0,0}, mi = 0, bw = 0;")
+    chains = gen_mont_mul(mod, dual=True)
+    o.append("#ifdef __CUDA_ARCH__")
+    o.append(body(chains, True))
+    o.append("#else")
+    o.append(body(chains, False))
+    o.append("#endif")
+    o.append("    for (int i = 0; i < 8; ++i) r[i] = bw ? ev[i] : t[i];")
+    o.append("}")
     # add
     o.append("ZK_FP_FN void %s_add(uint32_t* __restrict__ r, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b) {" % name)
     o.append("    uint32_t s[8] = {0,0,0,0,0,0,0,0}, t[8] = {0,0,0,0,0,0,0,0}, bw = 0;")

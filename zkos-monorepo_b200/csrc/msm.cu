@@ -103,10 +103,14 @@ __global__ void k_msm_scatter(const fr_t* __restrict__ scalars, size_t total, Ms
 // buckets): one CTA per MSM histograms the signed digits, scans, and scatters with SHARED-memory atomics; it also
 // emits the bucket order by decreasing run length.  Replaces k_msm_count + k_msm_scan + k_msm_scatter + k_msm_order
 // and their global atomics (the scalars are read twice, from L2).
-__global__ void __launch_bounds__(1024) k_msm_sort_smem(const fr_t* __restrict__ scalars, MsmDims D, uint32_t* __restrict__ offsets,
+// CT: the window width as a compile-time constant (0 = run-time D.c): with CT the window loop unrolls and the limb index of
+// every digit is static, so the scalar stays in registers instead of a dynamically indexed local-memory array.
+template <unsigned CT>
+__global__ void __launch_bounds__(1024, 1) k_msm_sort_smem(const fr_t* __restrict__ scalars, MsmDims D, uint32_t* __restrict__ offsets,
                                                         uint32_t* __restrict__ entries, uint32_t* __restrict__ order) {
     extern __shared__ uint32_t sm_sort[];
     const unsigned K = D.G * D.nb, T = blockDim.x;
+    const unsigned c = CT ? CT : D.c, W = CT ? 254 / CT + 1 : D.W;
     uint32_t* cnt = sm_sort;              // [K]    histogram -> cursors
     uint32_t* part = sm_sort + K;         // [T]
     uint32_t* hist = part + T;            // [heavy + 2] run-length histogram for the ordering
@@ -118,9 +122,29 @@ __global__ void __launch_bounds__(1024) k_msm_sort_smem(const fr_t* __restrict__
     for (unsigned i = threadIdx.x; i < K; i += T) cnt[i] = 0;
     for (unsigned i = threadIdx.x; i < D.heavy + 2; i += T) hist[i] = 0;
     __syncthreads();
-    for (unsigned i = threadIdx.x; i < D.n; i += T) {
-        fr_t s = from_mont(fe_load(sc + i));
-        for_each_digit(s.l, D.c, D.W, [&](unsigned w, uint32_t mag, bool) { atomicAdd(&cnt[(D.precomp ? 0 : w) * D.nb + (mag - 1)], 1u); });
+    // Histogram.  The digit loop is warp-uniform (every lane walks all W windows of its scalar, zero digits included), so the
+    // lanes can vote: a column whose scalars are all equal — a constant grand product, a selector — sends every lane of a warp
+    // to the SAME counter in every window, and 32 same-address shared atomics serialise.  When the voting lanes agree on the
+    // key, one lane adds their count (warp-aggregated atomic); otherwise every lane issues its own.
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t hmax = 1u << (c - 1);
+    for (unsigned base = 0; base < D.n; base += T) {
+        const unsigned i = base + threadIdx.x;
+        const bool valid = i < D.n;
+        fr_t s = valid ? from_mont(fe_load(sc + i)) : fr_t::zero();
+        uint32_t carry = 0;
+#pragma unroll
+        for (unsigned w = 0; w < W; ++w) {
+            uint32_t d = get_bits(s.l, w * c, c) + carry, mag;
+            if (d > hmax) { carry = 1; mag = (1u << c) - d; } else { carry = 0; mag = d; }
+            const bool nz = mag != 0;
+            const unsigned key = (D.precomp ? 0 : w) * D.nb + (mag - 1);
+            const unsigned am = __ballot_sync(0xffffffffu, nz);
+            if (!am) continue;
+            const unsigned key0 = __shfl_sync(0xffffffffu, key, __ffs(am) - 1);
+            if (__all_sync(0xffffffffu, !nz || key == key0)) { if (lane == (unsigned)__ffs(am) - 1) atomicAdd(&cnt[key0], (uint32_t)__popc(am)); }
+            else if (nz) atomicAdd(&cnt[key], 1u);
+        }
     }
     __syncthreads();
     // run-length histogram, then exclusive scan of the counts (in place) -> offsets
@@ -148,13 +172,32 @@ __global__ void __launch_bounds__(1024) k_msm_sort_smem(const fr_t* __restrict__
     }
     if (threadIdx.x == T - 1) om[K] = part[T - 1];
     __syncthreads();
-    for (unsigned i = threadIdx.x; i < D.n; i += T) {
-        fr_t s = from_mont(fe_load(sc + i));
-        for_each_digit(s.l, D.c, D.W, [&](unsigned w, uint32_t mag, bool negative) {
-            uint32_t pos = atomicAdd(&cnt[(D.precomp ? 0 : w) * D.nb + (mag - 1)], 1u);
-            uint32_t ref = D.precomp ? w * D.tstride + i : i;
-            em[pos] = ref | (negative ? 0x80000000u : 0u);
-        });
+    for (unsigned base = 0; base < D.n; base += T) {
+        const unsigned i = base + threadIdx.x;
+        const bool valid = i < D.n;
+        fr_t s = valid ? from_mont(fe_load(sc + i)) : fr_t::zero();
+        uint32_t carry = 0;
+#pragma unroll
+        for (unsigned w = 0; w < W; ++w) {
+            uint32_t d = get_bits(s.l, w * c, c) + carry, mag;
+            bool negative;
+            if (d > hmax) { carry = 1; mag = (1u << c) - d; negative = true; } else { carry = 0; mag = d; negative = false; }
+            const bool nz = mag != 0;
+            const unsigned key = (D.precomp ? 0 : w) * D.nb + (mag - 1);
+            const unsigned am = __ballot_sync(0xffffffffu, nz);
+            if (!am) continue;
+            const unsigned leader = __ffs(am) - 1;
+            const unsigned key0 = __shfl_sync(0xffffffffu, key, leader);
+            uint32_t pos = 0;
+            if (__all_sync(0xffffffffu, !nz || key == key0)) {
+                if (lane == leader) pos = atomicAdd(&cnt[key0], (uint32_t)__popc(am));
+                pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(am & ((1u << lane) - 1u));
+            } else if (nz) pos = atomicAdd(&cnt[key], 1u);
+            if (nz) {
+                uint32_t ref = D.precomp ? w * D.tstride + i : i;
+                em[pos] = ref | (negative ? 0x80000000u : 0u);
+            }
+        }
     }
 }
 
@@ -419,31 +462,48 @@ __global__ void __launch_bounds__(128) k_msm_buckets_split(const g1_affine_t* __
     if (live && !heavy && lane == 0) xyzz_store(buckets + idx, part[threadIdx.x]);
 }
 
-// block per (m, g); T = blockDim.x threads, each owns L = nb/T consecutive buckets
+// block per (m, g); T = blockDim.x threads, each owns L = nb/T consecutive buckets (L a power of two).
+//   per thread:  S_t = sum_j B[lo+j],  W_t = sum_j (j+1) B[lo+j]   (running sums: 2L additions)
+//   group sum    sum_t (W_t + lo_t S_t),  lo_t = t L,   and   sum_t t S_t = sum_{u>=1} sfx[u]  with sfx the inclusive suffix sums of S
+// so the weights cost one suffix scan (log2 T additions, every lane busy, no data-dependent branches) and log2 L doublings,
+// instead of a per-thread double-and-add by lo_t whose add/skip pattern diverges inside every warp.
 #define ZK_REDUCE_T 128
 #define ZK_REDUCE_T_LAT 512   // few MSMs in flight: more, shorter segments per bucket group
 __global__ void __launch_bounds__(ZK_REDUCE_T_LAT) k_msm_reduce(const g1_xyzz_t* __restrict__ buckets, MsmDims D,
                                                                 g1_xyzz_t* __restrict__ groups) {
     extern __shared__ uint4 reduce_smem[];
     g1_xyzz_t* part = reinterpret_cast<g1_xyzz_t*>(reduce_smem);
-    const unsigned T = blockDim.x;
+    const unsigned T = blockDim.x, t = threadIdx.x;
     const unsigned L = D.nb / T;  // host guarantees T | nb
     const g1_xyzz_t* B = buckets + (size_t)blockIdx.x * D.nb;
-    unsigned lo = threadIdx.x * L;  // bucket index lo has weight lo+1
+    unsigned lo = t * L;  // bucket index lo has weight lo+1
     g1_xyzz_t run = g1_xyzz_t::identity(), acc = g1_xyzz_t::identity();
     for (unsigned j = L; j-- > 0;) {
         run = xyzz_add(run, xyzz_load(B + lo + j));
         acc = xyzz_add(acc, run);
     }
-    // acc = sum_j (j+1) * B[lo+j]; the segment needs sum_j (lo+j+1) * B = acc + lo * run
-    if (lo) acc = xyzz_add(acc, xyzz_mul_small(run, lo));
-    part[threadIdx.x] = acc;
+    // inclusive suffix scan of the segment sums
+    part[t] = run;
     __syncthreads();
-    for (unsigned s = T >> 1; s > 0; s >>= 1) {
-        if (threadIdx.x < s) part[threadIdx.x] = xyzz_add(part[threadIdx.x], part[threadIdx.x + s]);
+    for (unsigned d = 1; d < T; d <<= 1) {
+        const bool has = t + d < T;
+        g1_xyzz_t other;
+        if (has) other = part[t + d];
+        __syncthreads();
+        if (has) { run = xyzz_add(run, other); part[t] = run; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) xyzz_store(groups + blockIdx.x, part[0]);
+    if (t >= 1) {
+        for (unsigned l = 1; l < L; l <<= 1) run = xyzz_dbl(run);
+        acc = xyzz_add(acc, run);
+    }
+    part[t] = acc;
+    __syncthreads();
+    for (unsigned s = T >> 1; s > 0; s >>= 1) {
+        if (t < s) part[t] = xyzz_add(part[t], part[t + s]);
+        __syncthreads();
+    }
+    if (t == 0) xyzz_store(groups + blockIdx.x, part[0]);
 }
 
 // Latency variant of the bucket reduction for a handful of MSMs: ZK_REDUCE_R CTAs of 128 threads share one bucket
@@ -599,9 +659,19 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
     const size_t sort_smem = (K + 1024 + D.heavy + 2) * sizeof(uint32_t);
     if (K <= 8192 && plan.n <= (1u << 20) && M >= 32) {   // one CTA per MSM: needs enough MSMs to fill the GPU
         KtScope kt(KT_MSM_SORT, st);
-        static DeviceOnce sort_once;
-        sort_once.run([] { ZK_CUDA(cudaFuncSetAttribute(k_msm_sort_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); });
-        ZK_LAUNCH(k_msm_sort_smem, (unsigned)M, 1024, sort_smem, st, d_scalars, D, ws.offsets.p, ws.entries.p, ws.order.p);
+        // measured (profiles/r02_ab_bench.md): 1024 threads 75 ms per 1024 proofs, 512 threads 116 ms, 256 threads 168 ms
+        static const unsigned sort_t = [] { const char* e = getenv("ZKGPU_SORT_T"); unsigned v = e ? (unsigned)atoi(e) : 0; return (v == 256 || v == 512 || v == 1024) ? v : 1024u; }();
+        switch (D.c) {
+#define ZK_SORT_CASE(CT)                                                                                                                          \
+    case CT: {                                                                                                                                    \
+        static DeviceOnce once;                                                                                                                   \
+        once.run([] { ZK_CUDA(cudaFuncSetAttribute(k_msm_sort_smem<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); });            \
+        ZK_LAUNCH(k_msm_sort_smem<CT>, (unsigned)M, sort_t, sort_smem, st, d_scalars, D, ws.offsets.p, ws.entries.p, ws.order.p);                 \
+    } break;
+            ZK_SORT_CASE(11) ZK_SORT_CASE(12) ZK_SORT_CASE(13) ZK_SORT_CASE(14)
+            default: ZK_SORT_CASE(0)
+#undef ZK_SORT_CASE
+        }
     } else {
         KtScope kt(KT_MSM_SORT, st);
         // the histogram is zeroed on the launching stream every call (k_msm_scatter counts it back down to zero, but a fresh

@@ -16,6 +16,7 @@
 // Coset scaling (zeta^(i mod 3), zeta^3 = 1), zero-padding and the 1/N factor of inverse transforms
 // are fused into the load / store of the passes.
 #include "ntt.cuh"
+#include <cooperative_groups.h>
 #include <map>
 #include <mutex>
 #include <array>
@@ -62,35 +63,12 @@ __device__ __forceinline__ void tile_st(uint4* sm, unsigned total, unsigned e, c
     sm[total + w] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
-// One tile pass.  Radix-2 DIT stages run three at a time on 8 register-resident elements per thread (12
-// butterflies between two __syncthreads), so a 256-point column costs 3 shared-memory round trips, not 8.
-template <int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) k_ntt_tile(const NttPass P) {
-    extern __shared__ uint4 sm4[];
+// The log_m radix-2 DIT stages of a tile already in shared memory (bit-reversed order).  Radix-2 stages run three at a
+// time on 8 register-resident elements per thread (12 butterflies between two __syncthreads), so a 256-point column costs
+// 3 shared-memory round trips, not 8.
+__device__ __forceinline__ void tile_stages(const NttPass& P, uint4* sm4) {
     const unsigned log_m = P.log_m, log_C = P.log_C;
-    const unsigned m = 1u << log_m, C = 1u << log_C, log_total = log_m + log_C, total = 1u << log_total;
-    const unsigned tile = blockIdx.x % P.tiles_per_poly;
-    const size_t poly = blockIdx.x / P.tiles_per_poly;
-    const fr_t* in = P.in + (poly / P.in_inner) * P.in_outer_stride + (poly % P.in_inner) * P.in_poly_stride + (size_t)tile * P.in_tile_stride;
-    fr_t* out = P.out + (poly / P.out_inner) * P.out_outer_stride + (poly % P.out_inner) * P.out_poly_stride + (size_t)tile * P.out_tile_stride;
-
-    for (unsigned el = threadIdx.x; el < total; el += blockDim.x) {
-        unsigned c, j;
-        if (P.c_fastest_in) { c = el & (C - 1); j = el >> log_C; } else { j = el & (m - 1); c = el >> log_m; }
-        size_t off = (size_t)j * P.in_sj + (size_t)c * P.in_sc;
-        size_t gi = (size_t)tile * P.in_tile_stride + off;  // index within the polynomial
-        const bool valid = gi < P.in_valid;
-        fr_t v = valid ? fe_load(in + off) : fr_t::zero();
-        if (P.pre_coset && valid) {
-            unsigned r3 = (unsigned)(gi % 3);
-            if (r3 == 1) v = v * P.cs1; else if (r3 == 2) v = v * P.cs2;
-        }
-        if (P.pre_table && valid) v = v * fe_ldg(P.pre_table + (((size_t)(poly % P.pre_count)) << P.log_N) + gi);
-        unsigned p = __brev(j) >> (32 - log_m);
-        tile_st(sm4, total, (p << log_C) | c, v);
-    }
-    __syncthreads();
-
+    const unsigned C = 1u << log_C, log_total = log_m + log_C, total = 1u << log_total;
     if (log_m >= 3) {
         const unsigned groups = total >> 3;
         for (unsigned done = 0; done < log_m;) {
@@ -156,6 +134,37 @@ __global__ void __launch_bounds__(MAXT, MINB) k_ntt_tile(const NttPass P) {
             __syncthreads();
         }
     }
+}
+
+// One tile pass.
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_ntt_tile(const NttPass P) {
+    extern __shared__ uint4 sm4[];
+    const unsigned log_m = P.log_m, log_C = P.log_C;
+    const unsigned m = 1u << log_m, C = 1u << log_C, log_total = log_m + log_C, total = 1u << log_total;
+    const unsigned tile = blockIdx.x % P.tiles_per_poly;
+    const size_t poly = blockIdx.x / P.tiles_per_poly;
+    const fr_t* in = P.in + (poly / P.in_inner) * P.in_outer_stride + (poly % P.in_inner) * P.in_poly_stride + (size_t)tile * P.in_tile_stride;
+    fr_t* out = P.out + (poly / P.out_inner) * P.out_outer_stride + (poly % P.out_inner) * P.out_poly_stride + (size_t)tile * P.out_tile_stride;
+
+    for (unsigned el = threadIdx.x; el < total; el += blockDim.x) {
+        unsigned c, j;
+        if (P.c_fastest_in) { c = el & (C - 1); j = el >> log_C; } else { j = el & (m - 1); c = el >> log_m; }
+        size_t off = (size_t)j * P.in_sj + (size_t)c * P.in_sc;
+        size_t gi = (size_t)tile * P.in_tile_stride + off;  // index within the polynomial
+        const bool valid = gi < P.in_valid;
+        fr_t v = valid ? fe_load(in + off) : fr_t::zero();
+        if (P.pre_coset && valid) {
+            unsigned r3 = (unsigned)(gi % 3);
+            if (r3 == 1) v = v * P.cs1; else if (r3 == 2) v = v * P.cs2;
+        }
+        if (P.pre_table && valid) v = v * fe_ldg(P.pre_table + (((size_t)(poly % P.pre_count)) << P.log_N) + gi);
+        unsigned p = __brev(j) >> (32 - log_m);
+        tile_st(sm4, total, (p << log_C) | c, v);
+    }
+    __syncthreads();
+
+    tile_stages(P, sm4);
 
     const size_t halfN = (size_t)1 << (P.log_N - 1);
     for (unsigned el = threadIdx.x; el < total; el += blockDim.x) {
@@ -178,6 +187,56 @@ __global__ void __launch_bounds__(MAXT, MINB) k_ntt_tile(const NttPass P) {
         if (P.has_scale) v = v * P.scale;
         fe_store(out + off, v);
     }
+}
+
+// Single-pass transform of N = 2^13 points by a CLUSTER of two CTAs (one SM each).  A polynomial of 8192 elements is 256 KB —
+// more than one SM's shared memory — so the four-step path above needed two launches, a scratch round trip through HBM/L2
+// and N inter-pass twiddle products.  Here CTA c of the pair loads the elements j = c (mod 2) (bit-reversed: the top position
+// bit), runs the first 12 stages in its own 128 KB tile — a size-4096 transform of the even / odd subsequence, E[k] and O[k] —
+// and the last radix-2 stage  X[k] = E[k] + w^k O[k],  X[k + N/2] = E[k] - w^k O[k]  reads the partner's tile through
+// distributed shared memory, each CTA producing (and storing, coalesced) half of the k range.  Same fused options as the
+// tile passes (coset scaling, per-element pre-multiplier, zero padding, 1/N).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) k_ntt_cluster2(const NttPass P) {
+    extern __shared__ uint4 sm4[];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    const unsigned total = 1u << P.log_m;          // log_m = log_N - 1, log_C = 0
+    const size_t poly = blockIdx.x >> 1;
+    const fr_t* in = P.in + (poly / P.in_inner) * P.in_outer_stride + (poly % P.in_inner) * P.in_poly_stride;
+    fr_t* out = P.out + (poly / P.out_inner) * P.out_outer_stride + (poly % P.out_inner) * P.out_poly_stride;
+    for (unsigned el = threadIdx.x; el < total; el += blockDim.x) {
+        const size_t gi = 2 * (size_t)el + rank;   // index within the polynomial
+        const bool valid = gi < P.in_valid;
+        fr_t v = valid ? fe_load(in + gi) : fr_t::zero();
+        if (P.pre_coset && valid) {
+            unsigned r3 = (unsigned)(gi % 3);
+            if (r3 == 1) v = v * P.cs1; else if (r3 == 2) v = v * P.cs2;
+        }
+        if (P.pre_table && valid) v = v * fe_ldg(P.pre_table + (((size_t)(poly % P.pre_count)) << P.log_N) + gi);
+        tile_st(sm4, total, __brev(el) >> (32 - P.log_m), v);
+    }
+    __syncthreads();
+    tile_stages(P, sm4);
+    cluster.sync();   // both halves transformed (and every input consumed: in-place transforms may now be overwritten)
+    const uint4* even = rank == 0 ? sm4 : cluster.map_shared_rank(sm4, 0);
+    const uint4* odd = rank == 1 ? sm4 : cluster.map_shared_rank(sm4, 1);
+    const unsigned half = total >> 1;
+    for (unsigned i = threadIdx.x; i < half; i += blockDim.x) {
+        const unsigned k = rank * half + i;
+        fr_t e = tile_ld(even, total, k), t = tile_ld(odd, total, k);
+        if (k) t = t * fe_ldg(P.tw + k);
+        fr_t lo = e + t, hi = e - t;
+        if (P.post_coset) {
+            const unsigned r_lo = k % 3, r_hi = (k + total) % 3;
+            if (r_lo == 1) lo = lo * P.cs1; else if (r_lo == 2) lo = lo * P.cs2;
+            if (r_hi == 1) hi = hi * P.cs1; else if (r_hi == 2) hi = hi * P.cs2;
+        }
+        if (P.has_scale) { lo = lo * P.scale; hi = hi * P.scale; }
+        fe_store(out + k, lo);
+        fe_store(out + k + total, hi);
+    }
+    cluster.sync();   // the partner may still be reading this CTA's tile
 }
 
 // tw[i] = w^i for i < count, from pows[b] = w^(2^b)
@@ -292,7 +351,16 @@ static unsigned pick_swz(unsigned log_m, unsigned log_C) {
     return q;
 }
 
+// 2^13 (Shielder's MAX_K) runs as one launch of two-CTA clusters when there are enough polynomials to give every SM a CTA
+// (measured, profiles/r02_ab_bench.md: 235.7 -> 230.4 ms per 1024 proofs; for the few transforms of a single proof the two-pass
+// path has more CTAs in flight and is faster).  ZKGPU_NTT_CLUSTER=0 falls back to the two-pass path everywhere.
+static bool ntt_use_cluster() {
+    static const bool on = [] { const char* e = getenv("ZKGPU_NTT_CLUSTER"); return e ? atoi(e) != 0 : true; }();
+    return on;
+}
+
 size_t ntt_scratch_elems(unsigned log_n, size_t batch) {
+    if (log_n == NTT_CLUSTER_LOG && ntt_use_cluster() && batch >= NTT_CLUSTER_MIN_BATCH) return 0;
     return log_n > NTT_SINGLE_PASS_MAX_LOG ? batch << log_n : 0;
 }
 
@@ -327,6 +395,20 @@ void ntt_run(const NttJob& J, cudaStream_t st) {
         P.has_scale = J.has_scale; P.scale = J.scale;
         P.first_window_trivial = (log_N >= 3 && P.in_valid * 8 <= N) ? 1 : 0;
         launch_pass(P, J.batch, st);
+        return;
+    }
+    if (log_N == NTT_CLUSTER_LOG && ntt_use_cluster() && J.batch >= NTT_CLUSTER_MIN_BATCH) {
+        P.in = J.in; P.out = J.out;
+        P.log_m = log_N - 1; P.log_C = 0; P.swz_q = pick_swz(P.log_m, 0);
+        P.tiles_per_poly = 1;
+        P.pre_coset = J.pre_coset; P.post_coset = J.post_coset;
+        P.has_scale = J.has_scale; P.scale = J.scale;
+        P.first_window_trivial = (P.in_valid * 8 <= N) ? 1 : 0;
+        ZK_REQUIRE(2 * J.batch < (1ull << 31), "ntt: grid too large");
+        static DeviceOnce once;
+        once.run([] { ZK_CUDA(cudaFuncSetAttribute(k_ntt_cluster2, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024)); });
+        KtScope kt(KT_NTT, st);
+        ZK_LAUNCH(k_ntt_cluster2, (unsigned)(2 * J.batch), 512, (size_t)128 * 1024, st, P);
         return;
     }
     ZK_REQUIRE(J.scratch != nullptr, "ntt: scratch buffer required for two-pass transforms");

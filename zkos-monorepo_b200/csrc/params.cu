@@ -99,6 +99,45 @@ static int params_setup_impl(uint32_t k, SmallRng& rng, uint64_t* g_out, uint64_
     catch (const std::exception& e) { g_last_error = e.what(); return ZKGPU_ERR_INTERNAL; }
 }
 
+// g_out[i] = s^(start + i) * G for i < count, s = the toxic scalar `ParamsKZG::setup` draws from SmallRng::seed_from_u64(seed):
+// a slice of the setup SRS, so a rank of a point-sharded MSM can build only its shard of the bases.
+extern "C" int zkgpu_setup_powers(uint64_t seed, uint64_t start, size_t count, uint64_t* g_out) {
+    try {
+        DeviceScope api_scope_(rt().primary());
+        Context& C = api_scope_.C;
+        ZK_REQUIRE(g_out || count == 0, "null pointer");
+        ZK_REQUIRE(count <= ((size_t)1 << 26), "setup_powers: at most 2^26 points per call");
+        if (!count) return ZKGPU_OK;
+        cudaStream_t st = C.stream;
+        SmallRng rng(seed);
+        uint64_t w[8];
+        for (int i = 0; i < 8; ++i) w[i] = rng.next_u64();
+        fr_t lo, hi;
+        for (int i = 0; i < 4; ++i) {
+            lo.l[2 * i] = (uint32_t)w[i]; lo.l[2 * i + 1] = (uint32_t)(w[i] >> 32);
+            hi.l[2 * i] = (uint32_t)w[4 + i]; hi.l[2 * i + 1] = (uint32_t)(w[4 + i] >> 32);
+        }
+        fr_reduce_raw(lo); fr_reduce_raw(hi);
+        fr_t r2 = fe_r2<FrTag>();
+        fr_t s = lo * r2 + hi * (r2 * r2);
+        std::vector<fr_t> pows(count);
+        fr_t cur = fr_pow_u64(s, start);
+        for (size_t i = 0; i < count; ++i) { pows[i] = cur; cur = cur * s; }
+        g1_affine_t G;
+        G.x = fq_t::zero(); G.y = fq_t::zero();
+        G.x.l[0] = 1; G.y.l[0] = 2;
+        G.x = to_mont(G.x); G.y = to_mont(G.y);
+        C.fr_buf.ensure(count); C.xyzz_buf.ensure(count); C.pt_buf.ensure(count);
+        ZK_CUDA(cudaMemcpyAsync(C.fr_buf.p, pows.data(), count * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+        ZK_LAUNCH(k_fixed_base_mul, ceil_div(count, 64), 64, 0, st, C.fr_buf.p, G, C.xyzz_buf.p, count);
+        g1_normalize(C.xyzz_buf.p, C.pt_buf.p, count, st);
+        ZK_CUDA(cudaMemcpyAsync(g_out, C.pt_buf.p, count * 64, cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(cudaStreamSynchronize(st));
+        return ZKGPU_OK;
+    } catch (const zk::Error& e) { g_last_error = e.what(); return e.code; }
+    catch (const std::exception& e) { g_last_error = e.what(); return ZKGPU_ERR_INTERNAL; }
+}
+
 extern "C" int zkgpu_params_setup(uint32_t k, uint64_t seed, uint64_t* g_out, uint64_t* g_lagrange_out) {
     SmallRng rng(seed);
     return params_setup_impl(k, rng, g_out, g_lagrange_out);

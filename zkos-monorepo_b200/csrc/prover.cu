@@ -254,8 +254,9 @@ static const size_t SCRATCH_ELEMS = (size_t)1 << 25;  // 1 GiB of two-pass NTT s
 
 // lagrange_to_coeff on `count` contiguous polynomials of 2^k values, in place
 static void intt_n(PkEntry& pk, ProverWs& W, fr_t* p, size_t count, cudaStream_t st) {
-    size_t per = pk.k > NTT_SINGLE_PASS_MAX_LOG ? std::max<size_t>(1, SCRATCH_ELEMS >> pk.k) : count;
-    if (pk.k > NTT_SINGLE_PASS_MAX_LOG) W.scratch.ensure(std::min(count, per) << pk.k);
+    const bool two = ntt_scratch_elems(pk.k, 1) != 0;   // two-pass transforms stage through a scratch buffer, chunk by chunk
+    size_t per = two ? std::max<size_t>(1, SCRATCH_ELEMS >> pk.k) : count;
+    if (two) W.scratch.ensure(std::min(count, per) << pk.k);
     for (size_t off = 0; off < count; off += per) {
         NttJob J;
         J.in = J.out = p + (off << pk.k); J.scratch = W.scratch.p; J.batch = std::min(per, count - off); J.log_n = pk.k;
@@ -266,7 +267,7 @@ static void intt_n(PkEntry& pk, ProverWs& W, fr_t* p, size_t count, cudaStream_t
 // coefficients -> values on the Qc quotient cosets: groups x cols polynomials at in[(g*cols + c)*n] -> out[g*out_group_stride + c*cn],
 // each output column coset-major [Qc][n].  Every coset is one size-n NTT of a[m] * g_c^m (table pk.coset_pows).
 static void coset_ext(PkEntry& pk, ProverWs& W, const fr_t* in, fr_t* out, size_t groups, size_t cols, size_t out_group_stride, cudaStream_t st) {
-    const bool two = pk.k > NTT_SINGLE_PASS_MAX_LOG;
+    const bool two = ntt_scratch_elems(pk.k, 1) != 0;
     const size_t per_group = cols * pk.Qc;
     size_t per = two ? std::max<size_t>(1, (SCRATCH_ELEMS >> pk.k) / per_group) : groups;
     if (two) W.scratch.ensure((std::min(groups, per) * per_group) << pk.k);

@@ -148,6 +148,48 @@ def g1_sum(points):
     return out
 
 
+def setup_powers(seed, start, count):
+    """g[i] = s^(start + i) * G, i < count: a slice of ParamsKZG::setup(.., SmallRng::seed_from_u64(seed)).g"""
+    g = np.empty((count, 8), dtype=np.uint64)
+    _chk(lib().zkgpu_setup_powers(C.c_uint64(seed), C.c_uint64(start), C.c_size_t(count), _p(g)))
+    return g
+
+
+def eval_polynomial(coeffs, x):
+    """halo2_proofs::arithmetic::eval_polynomial: sum_i coeffs[i] x^i"""
+    coeffs, x = _u64(coeffs), _u64(x)
+    out = np.empty(4, dtype=np.uint64)
+    _chk(lib().zkgpu_eval_polynomial(_p(coeffs), C.c_size_t(coeffs.size // 4), _p(x), _p(out)))
+    return out
+
+
+class Bases:
+    """best_multiexp over RESIDENT bases: the points are split into contiguous shards, one per selected device (a device only
+    ever holds its shard); every MSM reduces each shard to one point and sums the partial points on the primary device."""
+
+    def __init__(self, bases):
+        bases = _u64(bases)
+        self.n = bases.size // 8
+        h = C.c_uint64(0)
+        _chk(lib().zkgpu_bases_register(_p(bases), C.c_size_t(self.n), C.byref(h)))
+        self.handle = h.value
+        self.kernel_ms = 0.0
+
+    def msm(self, scalars=None):
+        """scalars (n, 4) in host memory, or None to reuse the scalars the previous call left in HBM; returns the affine point"""
+        out = np.zeros(12, dtype=np.uint64)
+        ms = C.c_double(0)
+        ptr = _p(_u64(scalars)) if scalars is not None else None
+        _chk(lib().zkgpu_msm_g1_bases(C.c_uint64(self.handle), ptr, C.c_size_t(self.n), _p(out), C.byref(ms)))
+        self.kernel_ms = ms.value
+        return _jac_to_affine(out)
+
+    def release(self):
+        if self.handle:
+            lib().zkgpu_bases_release(C.c_uint64(self.handle))
+            self.handle = 0
+
+
 class ParamsKZG:
     """Device-resident SRS: ParamsKZG::{commit, commit_lagrange}; `Blind` is ignored by KZG."""
 

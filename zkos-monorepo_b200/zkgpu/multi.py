@@ -2,9 +2,10 @@
 
 * Proof batches / request streams shard by rank (`shard_bounds`, `shard_round_robin`): proofs are independent,
   the SRS and the proving key are replicated.
-* The standalone large MSM splits its points into contiguous shards; every rank reduces its shard to ONE point
-  and the partial results (64 bytes each) are gathered and summed (`msm_sharded`).  The gather is the only
-  exchange step of the whole path; its payload is O(100 B) per GPU, so a plain all_gather is used.
+* The standalone large MSM splits its points into contiguous shards; every rank HOLDS ONLY ITS SHARD, reduces it to ONE
+  point, and the partial results (64 bytes each) are gathered and summed (`msm_sharded`).  The gather is the only
+  exchange step of the whole path; its payload is O(100 B) per GPU, so a plain all_gather is used.  (With several
+  devices in ONE process the library does the same with peer copies over NVLink: `zkgpu.Bases`, csrc/msm_sharded.cu.)
 Works with any torch.distributed backend (nccl on GPUs, gloo in the CPU tests).
 """
 import numpy as np
@@ -40,13 +41,11 @@ def gather_points(local_point, dist, device=None):
     return np.stack([o.cpu().numpy().view(np.uint64) for o in out])
 
 
-def msm_sharded(coeffs, bases, dist, local_msm, device=None):
-    """best_multiexp over all points with the points split across ranks.  `coeffs` / `bases` are the FULL
-    arrays (every rank holds or can index them); `local_msm(coeffs, bases)` computes one shard on this rank's
-    GPU (zkgpu.best_multiexp).  Returns the affine result on every rank."""
-    n = np.asarray(coeffs).reshape(-1, 4).shape[0]
-    lo, hi = shard_bounds(n, dist.get_rank(), dist.get_world_size())
-    c = np.asarray(coeffs).reshape(-1, 4)[lo:hi]
-    b = np.asarray(bases).reshape(-1, 8)[lo:hi]
-    part = local_msm(c, b) if hi > lo else np.zeros(8, dtype=np.uint64)
+def msm_sharded(shard_coeffs, shard_bases, dist, local_msm, device=None):
+    """best_multiexp over points split across ranks.  `shard_coeffs` / `shard_bases` are THIS RANK'S contiguous shard only
+    (`shard_bounds(n, rank, world)` of the whole problem; a rank never holds the other shards); `local_msm(coeffs, bases)`
+    reduces the shard to one affine point on this rank's GPU.  The 64-byte partial results are all-gathered and summed;
+    every rank returns the full result."""
+    c = np.asarray(shard_coeffs).reshape(-1, 4)
+    part = local_msm(c, np.asarray(shard_bases).reshape(-1, 8)) if c.shape[0] else np.zeros(8, dtype=np.uint64)
     return combine_partials(gather_points(part, dist, device))
