@@ -164,6 +164,14 @@ int zkgpu_msm_g1_srs_batch_dev(uint64_t srs, int basis, const void* d_scalars, s
  * halo2's `ConstraintSystem` and keygen `Assembly` hold after `Circuit::configure` / `synthesize`.
  * The SRS handle must have been registered with the same k (ParamsKZG::downsize first). */
 int zkgpu_pk_create(uint64_t srs, const uint8_t* circuit_blob, size_t blob_len, uint64_t* pk_out);
+/* ProvingKey::read for the artefact the reference ships: `pk_bin` = `k: u32 LE` ‖ `ProvingKey::to_bytes(RawBytesUnchecked)`
+ * (`marshall_pk`: /root/reference/crates/shielder_bindings/build.rs:19-33, read at src/circuits/mod.rs:35-48,89-101, cached by
+ * /root/reference/crates/shielder-cli/src/shielder_ops/pk.rs:68-126).  The file's fixed / permutation values, coefficient forms and
+ * extended cosets and the verifying key's commitments are used as they are (nothing is recomputed).  Upstream rebuilds the constraint
+ * system from the circuit TYPE; here `cs_blob` carries it: the same layout as `circuit_blob` with magic 0x5a4b4354, without the
+ * fixed assignment and copy constraints, followed by num_selectors: u32 and vk.transcript_repr() (32 bytes) — written by the Rust
+ * exporter shown in INTEGRATION.md (layout: zkgpu/circuits.py Circuit.cs_blob). */
+int zkgpu_pk_load(uint64_t srs, const uint8_t* cs_blob, size_t cs_blob_len, const uint8_t* pk_bin, size_t pk_bin_len, uint64_t* pk_out);
 int zkgpu_pk_release(uint64_t pk);
 /* info[0..14] = k, n, num_advice, num_fixed, degree, blinding_factors, num_perm_sets, num_quotients,
  *               num_evals, proof_len, extended_k, num_perm_columns, num_rotation_sets, sub_batch, replicas (devices) */
@@ -233,7 +241,8 @@ void zkgpu_set_trace(void (*fn)(const char* name, const void* data, size_t bytes
  * launching stream around every launch group of a class.  Slots: 0 MSM bucket accumulation, 1 MSM digit
  * sort (count/scan/scatter), 2 MSM bucket reduction, 3 NTT tile passes, 4 quotient evaluation,
  * 5 permutation / lookup grand products, 6 polynomial evaluation / SHPLONK algebra, 7 lookup compression +
- * permuted columns, 8 the rest (blinding scatter, ChaCha20 polynomial, affine normalisation). */
+ * permuted columns, 8 the rest (blinding scatter, ChaCha20 polynomial, affine normalisation), 9 device idle time at the
+ * Fiat-Shamir round trips (the host hashes the transcript; hidden by the other pipeline workers outside this timing mode). */
 void zkgpu_kernel_timing(int enable);
 int zkgpu_kernel_times(int slot, double* total_ms, uint64_t* launches, int reset);
 /* the library's CUDA stream (cudaStream_t) on the primary device after zkgpu_init, for event timing by the caller */

@@ -68,7 +68,7 @@ struct ConstraintSystem {
     // ConstraintSystem::degree(): permutation needs 3, gates their own degree
     // ConstraintSystem::degree(): permutation needs 3, a lookup max(4, 2 + input_degree + table_degree), gates their own
     unsigned degree() const {
-        unsigned d = perm_columns.empty() ? 1 : 3;
+        unsigned d = 3;   // permutation.required_degree(), whether or not a column is copy-enabled (halo2 ConstraintSystem::degree)
         for (auto& l : lookups) {
             unsigned di = 1, dt = 1;
             for (auto& e : l.inputs) di = std::max(di, expr_degree(e));

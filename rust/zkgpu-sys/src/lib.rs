@@ -45,6 +45,7 @@ extern "C" {
     pub fn zkgpu_merkle_root_batch(paths: *const u64, height: usize, m: usize, roots: *mut u64, consistent: *mut u8) -> c_int;
 
     pub fn zkgpu_pk_create(srs: u64, circuit_blob: *const u8, blob_len: usize, pk_out: *mut u64) -> c_int;
+    pub fn zkgpu_pk_load(srs: u64, cs_blob: *const u8, cs_blob_len: usize, pk_bin: *const u8, pk_bin_len: usize, pk_out: *mut u64) -> c_int;
     pub fn zkgpu_pk_release(pk: u64) -> c_int;
     pub fn zkgpu_pk_info(pk: u64, info: *mut u64) -> c_int;
     pub fn zkgpu_pk_vk(pk: u64, fixed_commitments: *mut u64, perm_commitments: *mut u64, digest: *mut u64) -> c_int;

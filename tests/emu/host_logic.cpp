@@ -47,3 +47,29 @@ void hl_inv(int field, int which, const uint32_t* a, uint32_t* out, size_t n) {
     }
 }
 }
+#include "pk_file.hpp"
+extern "C" {
+// pk.bin reader (csrc/pk_file.hpp) against a constraint-system-only blob: info = k, #fixed commitments, #perm commitments,
+// fixed_values count, fixed_cosets[0] length, perm_cosets count, l0 length; `first` receives the first element of
+// fixed_values[0], fixed_polys[0], fixed_cosets[0], perm_values[0], perm_cosets[last], l_active_row (6 x 8 u32)
+int hl_pk_file(const uint8_t* cs_blob, size_t cs_len, const uint8_t* pk_bin, size_t pk_len, uint64_t* info, uint32_t* first, char* err, size_t errlen) {
+    try {
+        CsDesc c = CsDesc::parse(cs_blob, cs_len);
+        if (!c.cs_only) throw std::runtime_error("not a constraint-system-only blob");
+        PkFile f = PkFile::parse(pk_bin, pk_len, c.num_fixed, c.perm_columns.size(), c.num_selectors, c.extended_k());
+        uint64_t v[7] = {f.k, f.fixed_commitments.size(), f.perm_commitments.size(), f.fixed_values.size(), f.fixed_cosets.empty() ? 0 : f.fixed_cosets[0].len,
+                         f.perm_cosets.size(), f.l0.len};
+        memcpy(info, v, sizeof v);
+        const uint8_t* src[6] = {f.fixed_values[0].p, f.fixed_polys[0].p, f.fixed_cosets[0].p, f.perm_values[0].p, f.perm_cosets.back().p, f.l_active_row.p};
+        for (int i = 0; i < 6; ++i) memcpy(first + 8 * i, src[i], 32);
+        memcpy(first + 48, c.transcript_repr.l, 32);
+        return 0;
+    } catch (const std::exception& e) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; return -1; }
+}
+// the prover's rng (csrc/host_util.hpp ProofRng): n u64 of mode 0 / 1 / 2; for mode 1 the advanced state is written back
+void hl_proof_rng(int mode, uint8_t* data, uint64_t* out, size_t n) {
+    ProofRng r(mode, data);
+    for (size_t i = 0; i < n; ++i) out[i] = r.next_u64();
+    r.store_state(data);
+}
+}

@@ -286,6 +286,14 @@ class PlonkOracle:
         _chk(lib().orc_plonk_vk(self.h, _p(fc), _p(pc), _p(dg)))
         return fc, pc, dg
 
+    def write_pk(self, num_selectors=0):
+        """`marshall_pk`: k u32 LE ‖ ProvingKey::to_bytes(RawBytesUnchecked), as the reference's build.rs writes pk.bin"""
+        ln = C.c_size_t(0)
+        _chk(lib().orc_plonk_write_pk(self.h, num_selectors, None, C.c_size_t(0), C.byref(ln)))
+        buf = C.create_string_buffer(ln.value)
+        _chk(lib().orc_plonk_write_pk(self.h, num_selectors, buf, ln, C.byref(ln)))
+        return buf.raw
+
     def check_witness(self, advice, instance):
         ok = C.c_int(0)
         advice, instance = np.ascontiguousarray(advice), np.ascontiguousarray(instance)

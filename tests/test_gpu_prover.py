@@ -349,3 +349,38 @@ def test_concurrent_api_callers_and_reinit(tiny):
     k2.release(); p2.release()
     pk.handle = 0; params.handle = 0                   # the module fixture's handles died with the shutdown
 
+
+
+@pytest.mark.parametrize("name", ["tiny_lookup", "small", "withdraw"])
+def test_pk_bin_round_trip(name):
+    """`unmarshall_pk` (/root/reference/crates/shielder_bindings/src/circuits/mod.rs:35-48): the oracle writes a pk.bin in halo2's
+    `ProvingKey::to_bytes(RawBytesUnchecked)` layout, zkgpu_pk_load takes the file's values / polys / cosets / commitments as they are
+    (plus the constraint-system-only blob) and proves byte-identically to the key that zkgpu_pk_create generated itself."""
+    zkgpu.init(0)
+    shape = circuits.Shape(name, k=11) if name == "withdraw" else circuits.Shape(name)
+    circ = circuits.Circuit(shape, O.OracleBackend, seed=5)
+    srs = O.downsized_srs(shape.k)
+    po = O.PlonkOracle(circ.blob, srs, threads=8)
+    params = zkgpu.ParamsKZG(shape.k, srs["g"], srs["g_lagrange"])
+    pk_gen = zkgpu.ProvingKey(params, circ.blob)
+    digest = pk_gen.vk()[2]
+    pk_file = zkgpu.ProvingKey(params, circ.cs_blob(digest, num_selectors=2), pk_bin=po.write_pk(2))
+    try:
+        for a, b in zip(pk_gen.vk(), pk_file.vk()):
+            assert np.array_equal(a, b)
+        assert pk_file.proof_len == pk_gen.proof_len and pk_file.num_evals == pk_gen.num_evals
+        wits = [circ.witness(40 + i) for i in range(3)]
+        adv = np.stack([w[0] for w in wits]); inst = np.stack([w[1] for w in wits])
+        seeds = np.array([11, 12, 13], dtype=np.uint64)
+        got = pk_file.prove_batch(adv, inst, seeds)
+        assert got == pk_gen.prove_batch(adv, inst, seeds)
+        assert got[0] == po.prove(adv[0], inst[0], seed=11) and po.verify(got[2], inst[2])
+        # the two blob kinds are not interchangeable
+        with pytest.raises(zkgpu.ZkGpuError):
+            zkgpu.ProvingKey(params, circ.blob, pk_bin=po.write_pk(0))
+        with pytest.raises(zkgpu.ZkGpuError):
+            zkgpu.ProvingKey(params, circ.cs_blob(digest))
+        with pytest.raises(zkgpu.ZkGpuError):
+            zkgpu.ProvingKey(params, circ.cs_blob(digest, num_selectors=2), pk_bin=po.write_pk(2)[:-32])
+    finally:
+        pk_file.release(); pk_gen.release(); params.release()

@@ -201,3 +201,84 @@ def test_quotient_from_cosets_identity():
         for m in range(n):
             got = sum(vinv[j][c] * pow(g[c], -m, p) * hhat[c][m] for c in range(Q)) % p
             assert got == h[j * n + m]
+
+
+def test_proof_rng_modes(hl):
+    """csrc/host_util.hpp ProofRng: u64 seed = SmallRng::seed_from_u64, running state continues and is handed back,
+    32-byte seed = ChaCha20Rng::from_seed (rand_chacha 0.3.1) — each against the oracle's generators"""
+    out = np.empty(100, dtype=np.uint64)
+    seed = np.array([42], dtype=np.uint64)
+    hl.hl_proof_rng(0, seed.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_size_t(100))
+    assert np.array_equal(out, O.smallrng(42, 100)) and seed[0] == 42
+    state = O.smallrng_state(42)
+    hl.hl_proof_rng(1, state.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_size_t(60))
+    assert np.array_equal(out[:60], O.smallrng(42, 100)[:60])
+    hl.hl_proof_rng(1, state.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_size_t(40))
+    assert np.array_equal(out[:40], O.smallrng(42, 100)[60:]), "the state written back does not continue the stream"
+    key = np.arange(32, dtype=np.uint8)
+    hl.hl_proof_rng(2, key.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_size_t(100))
+    assert np.array_equal(out, O.chacha20(key.tobytes(), 100)) and np.array_equal(key, np.arange(32, dtype=np.uint8))
+
+
+def test_pk_bin_reader_against_the_oracle_writer(hl):
+    """`pk.bin` = k ‖ ProvingKey::to_bytes(RawBytesUnchecked) (build.rs:19-33): the product's reader (csrc/pk_file.hpp) locates every
+    section of a file the oracle wrote, with and without selector bit-vectors, and rejects truncated / padded files."""
+    shape = circuits.Shape("tiny_lookup")
+    circ = circuits.Circuit(shape, O.OracleBackend, seed=2)
+    po = O.PlonkOracle(circ.blob, O.downsized_srs(shape.k), threads=2)
+    digest = po.vk(len(shape.perm_columns))[2]
+    for nsel in (0, 3):
+        pk_bin = po.write_pk(nsel)
+        cs_blob = circ.cs_blob(digest, num_selectors=nsel)
+        info = np.zeros(7, dtype=np.uint64)
+        first = np.zeros(56, dtype=np.uint32)
+        err = C.create_string_buffer(256)
+        rc = hl.hl_pk_file(cs_blob, C.c_size_t(len(cs_blob)), pk_bin, C.c_size_t(len(pk_bin)), info.ctypes.data_as(C.c_void_p),
+                           first.ctypes.data_as(C.c_void_p), err, C.c_size_t(256))
+        assert rc == 0, err.value
+        en = 1 << shape.extended_k
+        assert info.tolist() == [shape.k, shape.num_fixed, len(shape.perm_columns), shape.num_fixed, en, len(shape.perm_columns), en]
+        f = first.view(np.uint64).reshape(7, 4)
+        assert np.array_equal(f[0], circ.fixed[0][0]), "fixed_values[0][0]"
+        assert np.array_equal(f[6], digest), "transcript_repr"
+        # the coefficient / extended forms are the oracle's own transforms of that column
+        coeffs = O.domain_op(shape.degree, shape.k, 0, circ.fixed[0])
+        assert np.array_equal(f[1], coeffs[0]) and np.array_equal(f[2], O.domain_op(shape.degree, shape.k, 2, coeffs)[0])
+        for bad in (pk_bin[:-1], pk_bin + b"\\0", pk_bin[:1000]):
+            assert hl.hl_pk_file(cs_blob, C.c_size_t(len(cs_blob)), bad, C.c_size_t(len(bad)), info.ctypes.data_as(C.c_void_p),
+                                 first.ctypes.data_as(C.c_void_p), err, C.c_size_t(256)) == -1
+    # a full circuit blob is not accepted where the constraint system alone is expected, and vice versa
+    assert hl.hl_pk_file(circ.blob, C.c_size_t(len(circ.blob)), pk_bin, C.c_size_t(len(pk_bin)), info.ctypes.data_as(C.c_void_p),
+                         first.ctypes.data_as(C.c_void_p), err, C.c_size_t(256)) == -1
+    i2 = np.zeros(10, dtype=np.uint64)
+    assert hl.hl_cs_info(cs_blob, C.c_size_t(len(cs_blob)), i2.ctypes.data_as(C.c_void_p), err, C.c_size_t(256)) == 0
+    assert int(i2[2]) == shape.degree and int(i2[9]) == shape.proof_len
+
+
+def test_corrupt_counts_are_rejected_before_allocation(hl):
+    """a blob whose query / gate / copy counts exceed what the blob can hold is refused (no multi-gigabyte resize)"""
+    shape = circuits.Shape("tiny")
+    blob = bytearray(circuits.Circuit(shape, O.OracleBackend, seed=1).blob)
+    info = np.zeros(10, dtype=np.uint64)
+    err = C.create_string_buffer(256)
+    blob[20:24] = (0xFFFFFFF0).to_bytes(4, "little")      # number of advice queries
+    assert hl.hl_cs_info(bytes(blob), C.c_size_t(len(blob)), info.ctypes.data_as(C.c_void_p), err, C.c_size_t(256)) == -1
+    assert b"count exceeds" in err.value or b"truncated" in err.value
+
+
+def test_degree_without_permutation_columns(hl):
+    """ConstraintSystem::degree() starts from the permutation argument's 3 even when no column is copy-enabled"""
+    import struct
+    s = circuits.Shape("tiny")
+    blob = [struct.pack("<5I", circuits.MAGIC, s.k, 1, 1, 1)]
+    blob.append(struct.pack("<IIi", 1, 0, 0)); blob.append(struct.pack("<IIi", 1, 0, 0)); blob.append(struct.pack("<IIi", 1, 0, 0))   # queries
+    blob.append(struct.pack("<I", 0))                                                  # constants
+    gate = [(circuits.OP_FIXED, 0), (circuits.OP_ADVICE, 0), (circuits.OP_MUL, 0)]
+    blob.append(struct.pack("<II", 1, len(gate))); blob.append(np.array(gate, dtype=np.uint32).tobytes())
+    blob.append(struct.pack("<I", 0)); blob.append(struct.pack("<I", 0))                # no permutation columns, no lookups
+    blob.append(np.zeros((s.n, 4), dtype=np.uint64).tobytes()); blob.append(struct.pack("<I", 0))
+    blob = b"".join(blob)
+    info = np.zeros(10, dtype=np.uint64)
+    err = C.create_string_buffer(256)
+    assert hl.hl_cs_info(blob, C.c_size_t(len(blob)), info.ctypes.data_as(C.c_void_p), err, C.c_size_t(256)) == 0, err.value
+    assert int(info[2]) == 3 and int(info[6]) == 2 and int(info[4]) == 1          # degree 3, two quotient pieces, chunk_len 1

@@ -35,7 +35,7 @@ extern std::atomic<uint64_t> g_launches;  // kernels launched by this library (z
 
 // Optional per-kernel-class device timing (zkgpu_kernel_timing): CUDA events recorded on the launching stream
 // around the launches of one class; read back with zkgpu_kernel_times.  Off by default (no events recorded).
-enum { KT_MSM_BUCKETS = 0, KT_MSM_SORT = 1, KT_MSM_REDUCE = 2, KT_NTT = 3, KT_EVAL_H = 4, KT_PERM = 5, KT_POLY = 6, KT_LOOKUP = 7, KT_MISC = 8, KT_SLOTS = 10 };
+enum { KT_MSM_BUCKETS = 0, KT_MSM_SORT = 1, KT_MSM_REDUCE = 2, KT_NTT = 3, KT_EVAL_H = 4, KT_PERM = 5, KT_POLY = 6, KT_LOOKUP = 7, KT_MISC = 8, KT_HOSTGAP = 9, KT_SLOTS = 10 };
 extern bool g_ktime_on;
 void ktime_begin(int slot, cudaStream_t st);
 void ktime_end(int slot, cudaStream_t st);

@@ -18,6 +18,7 @@ namespace zk {
 
 enum : uint32_t { OP_CONST = 0, OP_FIXED = 1, OP_ADVICE = 2, OP_INSTANCE = 3, OP_NEG = 4, OP_ADD = 5, OP_MUL = 6, OP_SCALE = 7 };
 enum : uint32_t { COL_ADVICE = 0, COL_FIXED = 1, COL_INSTANCE = 2 };
+static const uint32_t CS_ONLY_MAGIC = 0x5a4b4354u;
 struct ExprIns { uint32_t op, arg; };
 struct ColRef { uint32_t type, index; };
 struct QueryRef { uint32_t column; int32_t rotation; };
@@ -34,6 +35,12 @@ struct CsDesc {
     std::vector<fr_t> fixed;  // num_fixed * n, column-major
     std::vector<CopyRef> copies;
     std::vector<uint8_t> blob;
+    // constraint-system-only blobs (magic CS_ONLY_MAGIC, written by the Rust exporter of INTEGRATION.md next to a pk.bin): no fixed
+    // assignment and no copy constraints — those come from the pk.bin — but the selector count of the verifying key section and
+    // `vk.transcript_repr()`
+    bool cs_only = false;
+    uint32_t num_selectors = 0;
+    fr_t transcript_repr;
 
     size_t n() const { return (size_t)1 << k; }
     static unsigned expr_degree(const std::vector<ExprIns>& e) {
@@ -55,9 +62,10 @@ struct CsDesc {
         }
         return mx;
     }
-    // ConstraintSystem::degree(): permutation 3, lookup max(4, 2 + input_degree + table_degree), gates their own
+    // ConstraintSystem::degree(): starts from the permutation argument's required degree (3, whether or not any column is
+    // copy-enabled), lookups max(4, 2 + input_degree + table_degree), gates their own
     unsigned degree() const {
-        unsigned d = perm_columns.empty() ? 1 : 3;
+        unsigned d = 3;
         for (auto& l : lookups) {
             unsigned di = 1, dt = 1;
             for (auto& e : l.inputs) di = std::max(di, expr_degree(e));
@@ -96,15 +104,19 @@ struct CsDesc {
         const uint8_t* p = data; const uint8_t* end = data + len;
         auto u32 = [&]() { ZK_REQUIRE(p + 4 <= end, "circuit blob: truncated"); uint32_t v; memcpy(&v, p, 4); p += 4; return v; };
         auto fr = [&]() { ZK_REQUIRE(p + 32 <= end, "circuit blob: truncated"); fr_t v; memcpy(v.l, p, 32); p += 32; return v; };
-        ZK_REQUIRE(u32() == 0x5a4b4353u, "circuit blob: bad magic");
+        const uint32_t magic = u32();
+        ZK_REQUIRE(magic == 0x5a4b4353u || magic == CS_ONLY_MAGIC, "circuit blob: bad magic");
+        c.cs_only = magic == CS_ONLY_MAGIC;
+        // every count below is bounded by what the rest of the blob can hold (8 bytes per query / instruction / column)
+        auto bounded = [&](uint32_t m, size_t each) { ZK_REQUIRE((size_t)(end - p) / each >= m, "circuit blob: count exceeds the blob"); return m; };
         c.k = u32(); c.num_fixed = u32(); c.num_advice = u32(); c.num_instance = u32();
         ZK_REQUIRE(c.k >= 3 && c.k <= 20, "circuit: k out of range");
-        auto rq = [&](std::vector<QueryRef>& v) { uint32_t m = u32(); v.resize(m); for (auto& q : v) { q.column = u32(); q.rotation = (int32_t)u32(); } };
+        auto rq = [&](std::vector<QueryRef>& v) { uint32_t m = bounded(u32(), 8); v.resize(m); for (auto& q : v) { q.column = u32(); q.rotation = (int32_t)u32(); } };
         rq(c.advice_queries); rq(c.fixed_queries); rq(c.instance_queries);
-        uint32_t nc = u32(); c.constants.resize(nc); for (auto& f : c.constants) f = fr();
-        uint32_t ng = u32(); c.gates.resize(ng);
-        for (auto& g : c.gates) { uint32_t m = u32(); g.resize(m); for (auto& i : g) { i.op = u32(); i.arg = u32(); } }
-        uint32_t np = u32(); c.perm_columns.resize(np); for (auto& pc : c.perm_columns) { pc.type = u32(); pc.index = u32(); }
+        uint32_t nc = bounded(u32(), 32); c.constants.resize(nc); for (auto& f : c.constants) f = fr();
+        uint32_t ng = bounded(u32(), 4); c.gates.resize(ng);
+        for (auto& g : c.gates) { uint32_t m = bounded(u32(), 8); g.resize(m); for (auto& i : g) { i.op = u32(); i.arg = u32(); } }
+        uint32_t np = bounded(u32(), 8); c.perm_columns.resize(np); for (auto& pc : c.perm_columns) { pc.type = u32(); pc.index = u32(); }
         auto rexpr = [&](std::vector<ExprIns>& g) { uint32_t m = u32(); ZK_REQUIRE(m <= 4096, "expression too long"); g.resize(m); for (auto& i : g) { i.op = u32(); i.arg = u32(); } };
         uint32_t nl = u32(); ZK_REQUIRE(nl <= 64, "too many lookups"); c.lookups.resize(nl);
         for (auto& l : c.lookups) {
@@ -113,11 +125,16 @@ struct CsDesc {
         }
         ZK_REQUIRE(c.num_instance == 1, "exactly one instance column is supported (as in Shielder's circuits)");
         size_t n = c.n();
-        ZK_REQUIRE((size_t)(end - p) >= (size_t)c.num_fixed * n * 32, "circuit blob: truncated fixed columns");
-        c.fixed.resize((size_t)c.num_fixed * n);
-        memcpy(c.fixed.data(), p, c.fixed.size() * 32); p += c.fixed.size() * 32;
-        uint32_t ncp = u32(); c.copies.resize(ncp);
-        for (auto& cp : c.copies) { cp.lcol = u32(); cp.lrow = u32(); cp.rcol = u32(); cp.rrow = u32(); }
+        if (c.cs_only) {
+            c.num_selectors = u32();
+            c.transcript_repr = fr();
+        } else {
+            ZK_REQUIRE((size_t)(end - p) >= (size_t)c.num_fixed * n * 32, "circuit blob: truncated fixed columns");
+            c.fixed.resize((size_t)c.num_fixed * n);
+            memcpy(c.fixed.data(), p, c.fixed.size() * 32); p += c.fixed.size() * 32;
+            uint32_t ncp = bounded(u32(), 16); c.copies.resize(ncp);
+            for (auto& cp : c.copies) { cp.lcol = u32(); cp.lrow = u32(); cp.rcol = u32(); cp.rrow = u32(); }
+        }
         ZK_REQUIRE(p == end, "circuit blob: trailing bytes");
         // validation
         for (auto& q : c.advice_queries) ZK_REQUIRE(q.column < c.num_advice, "advice query out of range");

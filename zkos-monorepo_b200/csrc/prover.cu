@@ -23,6 +23,7 @@
 #include "prover_kernels.cuh"
 #include "plonk_types.hpp"
 #include "host_util.hpp"
+#include "pk_file.hpp"
 #include <map>
 #include <atomic>
 #include <set>
@@ -340,12 +341,18 @@ static void trace_dev(const char* name, const fr_t* d, size_t count, size_t reps
 // ---------------------------------------------------------------------------------------------
 // keygen_vk + keygen_pk
 // ---------------------------------------------------------------------------------------------
-static std::unique_ptr<PkEntry> keygen(Context& C, uint64_t srs_handle, const uint8_t* blob, size_t len) {
+// `file` == nullptr: keygen_vk + keygen_pk from the circuit blob's fixed assignment and copy constraints.
+// `file` != nullptr: ProvingKey::read — the blob carries the constraint system only and every assignment-derived part (fixed / sigma
+// values, coefficient forms, extended cosets, l_0 / l_last / l_active_row, the verifying key's commitments) is taken from the pk.bin
+// instead of being recomputed: no commitments, no transforms, only a gather of the quotient cosets out of the file's extended domain.
+static std::unique_ptr<PkEntry> keygen(Context& C, uint64_t srs_handle, const uint8_t* blob, size_t len, const uint8_t* pk_bin = nullptr, size_t pk_bin_len = 0) {
     std::unique_ptr<PkEntry> pkp(new PkEntry);
     PkEntry& pk = *pkp;
     pk.C = &C;
     pk.cs = CsDesc::parse(blob, len);
     const CsDesc& cs = pk.cs;
+    ZK_REQUIRE(cs.cs_only == (pk_bin != nullptr), pk_bin ? "pk_load: expected a constraint-system-only blob (the assignment comes from the pk.bin)"
+                                                          : "pk_create: the blob has no fixed assignment; use zkgpu_pk_load with the pk.bin");
     SrsEntry& S = C.get_srs(srs_handle);
     ZK_REQUIRE(S.k == cs.k, "keygen: params.k != circuit k (downsize the params first)");
     pk.srs_handle = srs_handle;
@@ -421,45 +428,76 @@ static std::unique_ptr<PkEntry> keygen(Context& C, uint64_t srs_handle, const ui
         intt_n(pk, pk.ws[0], polys.p, count, st);
         coset_ext(pk, pk.ws[0], polys.p, ext.p, 1, count, count * en, st);
     };
-    // fixed columns
-    pk.fixed_vals.alloc(std::max<size_t>(1, pk.F * n));
-    h2d(pk.fixed_vals.p, cs.fixed, st);
-    commit_cols(pk.fixed_vals.p, pk.F, pk.fixed_commitments);
-    polys_and_cosets(pk.fixed_vals, pk.fixed_polys, pk.fixed_ext, pk.F);
-    // permutation: sigma columns hold delta^col * omega^row of the mapped cell
-    {
-        PermAssembly as(pk.S, n);
-        for (auto& cp : cs.copies) as.copy(cp.lcol, cp.lrow, cp.rcol, cp.rrow);
+    if (pk_bin) {
+        PkFile f = PkFile::parse(pk_bin, pk_bin_len, pk.F, pk.S, cs.num_selectors, pk.ek);
+        ZK_REQUIRE(f.k == pk.k, "pk_load: pk.bin was generated for another k");
+        pk.fixed_commitments = f.fixed_commitments; pk.perm_commitments = f.perm_commitments;
+        const unsigned log_e = pk.ek - pk.k;   // the extended domain is the union of 2^log_e cosets g_c H; coset c = entries c + 2^log_e j
+        DevBuf<fr_t> stage(pk.en);
+        auto column = [&](const PkFile::Poly& q, fr_t* dst) { ZK_CUDA(cudaMemcpyAsync(dst, q.p, n * sizeof(fr_t), cudaMemcpyHostToDevice, st)); };
+        auto cosets = [&](const PkFile::Poly& q, fr_t* dst) {
+            ZK_CUDA(cudaMemcpyAsync(stage.p, q.p, pk.en * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+            launch_gather_cosets(stage.p, dst, pk.k, log_e, pk.Qc, st);
+        };
+        auto group = [&](const std::vector<PkFile::Poly>& vals, const std::vector<PkFile::Poly>& polys, const std::vector<PkFile::Poly>& ext,
+                         DevBuf<fr_t>& d_vals, DevBuf<fr_t>& d_polys, DevBuf<fr_t>& d_ext) {
+            const size_t count = vals.size();
+            d_vals.alloc(std::max<size_t>(1, count * n)); d_polys.alloc(std::max<size_t>(1, count * n)); d_ext.alloc(std::max<size_t>(1, count * en));
+            for (size_t c = 0; c < count; ++c) { column(vals[c], d_vals.p + c * n); column(polys[c], d_polys.p + c * n); cosets(ext[c], d_ext.p + c * en); }
+        };
+        group(f.fixed_values, f.fixed_polys, f.fixed_cosets, pk.fixed_vals, pk.fixed_polys, pk.fixed_ext);
+        group(f.perm_values, f.perm_polys, f.perm_cosets, pk.sigma_vals, pk.sigma_polys, pk.sigma_ext);
+        pk.l0.alloc(en); pk.l_last.alloc(en); pk.l_active.alloc(en);
+        cosets(f.l0, pk.l0.p); cosets(f.l_last, pk.l_last.p); cosets(f.l_active_row, pk.l_active.p);
         std::vector<fr_t> dp(std::max<unsigned>(1, pk.S));
         fr_t d = fe_one<FrTag>(), delta = fr_from_limbs(fr_consts::DELTA);
         for (unsigned c = 0; c < pk.S; ++c) { dp[c] = d; d = d * delta; }
         upload(pk.delta_pows, dp, st);
-        DevBuf<uint32_t> d_mc(std::max<size_t>(1, as.map_col.size())), d_mr(std::max<size_t>(1, as.map_row.size()));
-        h2d(d_mc.p, as.map_col, st); h2d(d_mr.p, as.map_row, st);
-        pk.sigma_vals.alloc(std::max<size_t>(1, pk.S * n));
-        launch_sigma_values(d_mc.p, d_mr.p, pk.delta_pows.p, pk.omega_tw, pk.sigma_vals.p, pk.S, pk.k, st);
-        ZK_CUDA(cudaStreamSynchronize(st));
-        commit_cols(pk.sigma_vals.p, pk.S, pk.perm_commitments);
-        polys_and_cosets(pk.sigma_vals, pk.sigma_polys, pk.sigma_ext, pk.S);
         std::vector<ColSrc> cols(std::max<unsigned>(1, pk.S));
         for (unsigned c = 0; c < pk.S; ++c) { cols[c].type = cs.perm_columns[c].type; cols[c].index = cs.perm_columns[c].index; }
         upload(pk.cols, cols, st);
-    }
-    // l_0, l_blind, l_last on the quotient cosets; l_active_row = 1 - l_last - l_blind
-    {
-        std::vector<fr_t> lag(3 * n, fr_t::zero());
-        fr_t one = fe_one<FrTag>();
-        lag[0] = one;
-        for (size_t i = n - pk.bf; i < n; ++i) lag[n + i] = one;
-        lag[2 * n + (n - pk.bf - 1)] = one;
-        DevBuf<fr_t> vals(3 * n), polys, ext;
-        h2d(vals.p, lag, st);
-        polys_and_cosets(vals, polys, ext, 3);
-        pk.l0.alloc(en); pk.l_last.alloc(en); pk.l_active.alloc(en);
-        ZK_CUDA(cudaMemcpyAsync(pk.l0.p, ext.p, en * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
-        ZK_CUDA(cudaMemcpyAsync(pk.l_last.p, ext.p + 2 * en, en * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
-        launch_one_minus_sum(ext.p + 2 * en, ext.p + en, pk.l_active.p, en, st);
         ZK_CUDA(cudaStreamSynchronize(st));
+    } else {
+        // fixed columns
+        pk.fixed_vals.alloc(std::max<size_t>(1, pk.F * n));
+        h2d(pk.fixed_vals.p, cs.fixed, st);
+        commit_cols(pk.fixed_vals.p, pk.F, pk.fixed_commitments);
+        polys_and_cosets(pk.fixed_vals, pk.fixed_polys, pk.fixed_ext, pk.F);
+        // permutation: sigma columns hold delta^col * omega^row of the mapped cell
+        {
+            PermAssembly as(pk.S, n);
+            for (auto& cp : cs.copies) as.copy(cp.lcol, cp.lrow, cp.rcol, cp.rrow);
+            std::vector<fr_t> dp(std::max<unsigned>(1, pk.S));
+            fr_t d = fe_one<FrTag>(), delta = fr_from_limbs(fr_consts::DELTA);
+            for (unsigned c = 0; c < pk.S; ++c) { dp[c] = d; d = d * delta; }
+            upload(pk.delta_pows, dp, st);
+            DevBuf<uint32_t> d_mc(std::max<size_t>(1, as.map_col.size())), d_mr(std::max<size_t>(1, as.map_row.size()));
+            h2d(d_mc.p, as.map_col, st); h2d(d_mr.p, as.map_row, st);
+            pk.sigma_vals.alloc(std::max<size_t>(1, pk.S * n));
+            launch_sigma_values(d_mc.p, d_mr.p, pk.delta_pows.p, pk.omega_tw, pk.sigma_vals.p, pk.S, pk.k, st);
+            ZK_CUDA(cudaStreamSynchronize(st));
+            commit_cols(pk.sigma_vals.p, pk.S, pk.perm_commitments);
+            polys_and_cosets(pk.sigma_vals, pk.sigma_polys, pk.sigma_ext, pk.S);
+            std::vector<ColSrc> cols(std::max<unsigned>(1, pk.S));
+            for (unsigned c = 0; c < pk.S; ++c) { cols[c].type = cs.perm_columns[c].type; cols[c].index = cs.perm_columns[c].index; }
+            upload(pk.cols, cols, st);
+        }
+        // l_0, l_blind, l_last on the quotient cosets; l_active_row = 1 - l_last - l_blind
+        {
+            std::vector<fr_t> lag(3 * n, fr_t::zero());
+            fr_t one = fe_one<FrTag>();
+            lag[0] = one;
+            for (size_t i = n - pk.bf; i < n; ++i) lag[n + i] = one;
+            lag[2 * n + (n - pk.bf - 1)] = one;
+            DevBuf<fr_t> vals(3 * n), polys, ext;
+            h2d(vals.p, lag, st);
+            polys_and_cosets(vals, polys, ext, 3);
+            pk.l0.alloc(en); pk.l_last.alloc(en); pk.l_active.alloc(en);
+            ZK_CUDA(cudaMemcpyAsync(pk.l0.p, ext.p, en * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+            ZK_CUDA(cudaMemcpyAsync(pk.l_last.p, ext.p + 2 * en, en * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+            launch_one_minus_sum(ext.p + 2 * en, ext.p + en, pk.l_active.p, en, st);
+            ZK_CUDA(cudaStreamSynchronize(st));
+        }
     }
     // t_evaluations (inverted): ((zeta * ext_omega^i)^n - 1)^-1, i < 2^(ek-k)
     {
@@ -503,8 +541,11 @@ static std::unique_ptr<PkEntry> keygen(Context& C, uint64_t srs_handle, const ui
         upload(pk.lk_prog, lprog, st); upload(pk.lk_expr_off, eoff, st); upload(pk.lk_off, loff, st);
         ZK_CUDA(cudaStreamSynchronize(st));
     }
-    // opaque vk digest (see oracle/plonk.hpp header): keccak(blob ‖ fixed commitments ‖ sigma commitments) mod r
-    {
+    // vk digest.  Upstream `transcript_repr` is a Blake2b hash of the verifying key's Rust Debug output: with a pk.bin it is the value
+    // the exporter wrote into the blob; for keys generated here it is an opaque constant, keccak(blob ‖ fixed commitments ‖ sigma
+    // commitments) mod r (see oracle/plonk.hpp header).
+    if (pk_bin) pk.digest = cs.transcript_repr;
+    else {
         std::vector<uint8_t> in(cs.blob);
         auto add = [&](const g1_affine_t& p) { uint8_t w[64]; fe_to_be_bytes(p.x, w); fe_to_be_bytes(p.y, w + 32); in.insert(in.end(), w, w + 64); };
         for (auto& p : pk.fixed_commitments) add(p);
@@ -675,13 +716,21 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
     h2d(W.raw_adv.p, raw_adv, st); h2d(W.raw_z.p, raw_z, st); h2d(W.seeds.p, cseeds, st);
     if (L) { h2d(W.raw_la.p, raw_la, st); h2d(W.raw_ls.p, raw_ls, st); h2d(W.raw_lz.p, raw_lz, st); ZK_CUDA(cudaMemsetAsync(W.d_error.p, 0, B * sizeof(int), st)); }
 
+    // Timing class KT_HOSTGAP (zkgpu_kernel_timing only): device time between the end of the work queued before a Fiat-Shamir round
+    // trip and the first operation the host queues after it — the GPU idles there when a single pipeline worker runs (the headline
+    // passes hide it behind the other workers' kernels).
+    bool gap_open = false;
+    auto gap_begin = [&]() { if (g_ktime_on && !gap_open) { ktime_begin(KT_HOSTGAP, st); gap_open = true; } };
+    auto gap_end = [&]() { if (gap_open) { ktime_end(KT_HOSTGAP, st); gap_open = false; } };
     auto fetch_points = [&](size_t count) -> const g1_affine_t* {
         ZK_CUDA(cudaMemcpyAsync(W.h_aff.p, W.aff.p, count * sizeof(g1_affine_t), cudaMemcpyDeviceToHost, st));
+        gap_begin();
         ZK_CUDA(cudaStreamSynchronize(st));
         return W.h_aff.as<g1_affine_t>();
     };
     std::vector<Challenges> ch(B);
     auto push_challenges = [&]() {
+        gap_end();
         for (size_t b = 0; b < B; ++b) { ch[b].theta = ps[b].theta; ch[b].beta = ps[b].beta; ch[b].gamma = ps[b].gamma; ch[b].y = ps[b].y; ch[b].x = ps[b].x; }
         h2d(W.ch.p, ch, st);
     };
@@ -842,6 +891,7 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
             outs[b] = W.hpoly.p + b * n;
         }
         off[B] = (uint32_t)(B * Q);
+        gap_end();
         upload(W.terms, terms, st); upload(W.job_off, off, st); upload(W.outs, outs, st);
         launch_lincomb(W.terms.p, W.job_off.p, W.outs.p, B, n, st);
 
@@ -882,6 +932,7 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
         upload(W.eval_jobs, jobs, st);
         launch_poly_eval(W.eval_jobs.p, W.evals.p, jobs.size(), pk.k, st);
         ZK_CUDA(cudaMemcpyAsync(W.h_evals.p, W.evals.p, jobs.size() * sizeof(fr_t), cudaMemcpyDeviceToHost, st));
+        gap_begin();
         ZK_CUDA(cudaStreamSynchronize(st));
         const fr_t* he = W.h_evals.as<fr_t>();
         for (size_t b = 0; b < B; ++b) {
@@ -973,6 +1024,7 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
             }
         }
         off.push_back((uint32_t)terms.size());
+        gap_end();
         upload(W.terms, terms, st); upload(W.job_off, off, st); upload(W.outs, outs, st);
         h2d(W.low.p, low, st);
         launch_lincomb(W.terms.p, W.job_off.p, W.outs.p, B * ns, n, st);
@@ -1040,6 +1092,7 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
             divs[b].in = W.lx.p + b * n; divs[b].out = W.tmp1.p + b * n; divs[b].pt = p.mu; divs[b].low = W.low.p + b * 4;
         }
         off[B] = (uint32_t)(B * (ns + 1));
+        gap_end();
         upload(W.terms, terms, st); upload(W.job_off, off, st); upload(W.outs, outs, st);
         h2d(W.low.p, low, st);
         launch_lincomb(W.terms.p, W.job_off.p, W.outs.p, B, n, st);
@@ -1054,6 +1107,7 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
             ZK_REQUIRE((size_t)(ps[b].tr.out - (proofs + b * pk.proof_len)) == pk.proof_len, "internal: proof length mismatch");
         }
     }
+    gap_end();
     // failed proofs: no bytes, only a status (the reference fails that request alone, tee/.../server.rs:189-190)
     for (size_t b = 0; b < B; ++b) {
         if (status[b] != PROOF_OK) memset(proofs + b * pk.proof_len, 0, pk.proof_len);
@@ -1244,7 +1298,7 @@ int zkgpu_set_rayon_threads(unsigned num_threads) {
     API_END
 }
 
-int zkgpu_pk_create(uint64_t srs, const uint8_t* circuit_blob, size_t blob_len, uint64_t* pk_out) {
+static int pk_create_or_load(uint64_t srs, const uint8_t* circuit_blob, size_t blob_len, const uint8_t* pk_bin, size_t pk_bin_len, uint64_t* pk_out) {
     API_TRY
     ZK_REQUIRE(circuit_blob && pk_out, "null pointer");
     Runtime& R = rt(); R.require();
@@ -1256,7 +1310,7 @@ int zkgpu_pk_create(uint64_t srs, const uint8_t* circuit_blob, size_t blob_len, 
     auto one = [&](size_t g) {
         try {
             DeviceScope scope(*R.devs[g]);
-            P->dev[g] = keygen(*R.devs[g], srs, circuit_blob, blob_len);
+            P->dev[g] = keygen(*R.devs[g], srs, circuit_blob, blob_len, pk_bin, pk_bin_len);
         } catch (...) { err[g] = std::current_exception(); }
     };
     if (G == 1) one(0);
@@ -1271,6 +1325,13 @@ int zkgpu_pk_create(uint64_t srs, const uint8_t* circuit_blob, size_t blob_len, 
     g_pks[h] = std::move(P);
     *pk_out = h;
     API_END
+}
+int zkgpu_pk_create(uint64_t srs, const uint8_t* circuit_blob, size_t blob_len, uint64_t* pk_out) {
+    return pk_create_or_load(srs, circuit_blob, blob_len, nullptr, 0, pk_out);
+}
+int zkgpu_pk_load(uint64_t srs, const uint8_t* cs_blob, size_t cs_blob_len, const uint8_t* pk_bin, size_t pk_bin_len, uint64_t* pk_out) {
+    if (!pk_bin) { g_last_error = "null pointer"; return ZKGPU_ERR_ARG; }
+    return pk_create_or_load(srs, cs_blob, cs_blob_len, pk_bin, pk_bin_len, pk_out);
 }
 int zkgpu_pk_release(uint64_t pk) {
     API_TRY

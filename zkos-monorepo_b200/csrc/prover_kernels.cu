@@ -443,8 +443,9 @@ void launch_sub_low(fr_t* const* polys, const fr_t* low, size_t num_jobs, cudaSt
 
 // q_{i-1} = a_i + pt * q_i  (i from n-1 down), i.e. Q_i = sum_{j>=i} a_j pt^(j-i), q[i-1] = Q_i
 #define ZK_DIV_T 128
-__global__ void __launch_bounds__(ZK_DIV_T) k_kate_div(const DivJob* jobs, unsigned k) {
-    __shared__ uint32_t sm[8 * ZK_DIV_T];
+#define ZK_DIV_T_LAT 512   // a handful of jobs (single proofs): more, shorter serial segments per polynomial
+__global__ void __launch_bounds__(ZK_DIV_T_LAT) k_kate_div(const DivJob* jobs, unsigned k) {
+    __shared__ uint32_t sm[8 * ZK_DIV_T_LAT];
     const size_t n = (size_t)1 << k;
     const unsigned T = blockDim.x, t = threadIdx.x;
     const unsigned L = (unsigned)(n / T);
@@ -495,7 +496,8 @@ __global__ void __launch_bounds__(ZK_DIV_T) k_kate_div(const DivJob* jobs, unsig
 void launch_kate_div(const DivJob* jobs, size_t num_jobs, unsigned k, cudaStream_t st) {
     if (!num_jobs) return;
     size_t n = (size_t)1 << k;
-    unsigned T = n >= ZK_DIV_T ? ZK_DIV_T : (unsigned)n;
+    unsigned T = num_jobs < 2 * 148 ? ZK_DIV_T_LAT : ZK_DIV_T;   // too few polynomials to fill the GPU: split each one finer
+    if (n < T) T = (unsigned)n;
     KtScope kt(KT_POLY, st);
     ZK_LAUNCH(k_kate_div, (unsigned)num_jobs, T, 0, st, jobs, k);
 }
@@ -533,6 +535,17 @@ void launch_sigma_values(const uint32_t* map_col, const uint32_t* map_row, const
     size_t total = S << k;
     if (total) ZK_LAUNCH(k_sigma_values, ceil_div(total, 128), 128, 0, st, map_col, map_row, delta_pows, omega_tw, out, total, k);
 }
+__global__ void k_gather_cosets(const fr_t* __restrict__ ext, fr_t* __restrict__ dst, unsigned k, unsigned log_e, size_t total) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const size_t c = t >> k, j = t & (((size_t)1 << k) - 1);
+    fe_store(dst + t, fe_load(ext + c + (j << log_e)));
+}
+void launch_gather_cosets(const fr_t* ext, fr_t* dst, unsigned k, unsigned log_e, unsigned Qc, cudaStream_t st) {
+    const size_t total = (size_t)Qc << k;
+    if (total) ZK_LAUNCH(k_gather_cosets, ceil_div(total, 128), 128, 0, st, ext, dst, k, log_e, total);
+}
+
 __global__ void k_one_minus_sum(const fr_t* a, const fr_t* b, fr_t* out, size_t n) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) fe_store(out + t, fe_one<FrTag>() - fe_load(a + t) - fe_load(b + t));

@@ -121,6 +121,9 @@ void launch_pull_from_host(void* dst, const void* mapped_src, size_t bytes, unsi
 // sigma values for keygen: out[c][row] = delta^{map_col} * omega^{map_row}
 void launch_sigma_values(const uint32_t* map_col, const uint32_t* map_row, const fr_t* delta_pows, const fr_t* omega_tw, fr_t* out,
                          size_t S, unsigned k, cudaStream_t st);
+// quotient cosets out of halo2's extended domain: dst[c * n + j] = ext[c + (j << log_e)], c < Qc, j < n = 2^k
+// (extended point i = zeta * ext_omega^i, so the entries i = c mod 2^log_e are the coset g_c * H in the order omega^j)
+void launch_gather_cosets(const fr_t* ext, fr_t* dst, unsigned k, unsigned log_e, unsigned Qc, cudaStream_t st);
 // out[i] = 1 - a[i] - b[i]
 void launch_one_minus_sum(const fr_t* a, const fr_t* b, fr_t* out, size_t n, cudaStream_t st);
 // elementwise helpers (also exported through the C ABI for synthetic witness generation):

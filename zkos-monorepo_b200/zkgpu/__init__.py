@@ -291,11 +291,17 @@ class ProvingKey:
     INFO = ("k", "n", "num_advice", "num_fixed", "degree", "blinding_factors", "num_perm_sets", "num_quotients",
             "num_evals", "proof_len", "extended_k", "num_perm_columns", "num_rotation_sets", "sub_batch", "replicas")
 
-    def __init__(self, params, circuit_blob):
+    def __init__(self, params, circuit_blob, pk_bin=None):
+        """keygen from a circuit blob, or — with `pk_bin` — `unmarshall_pk`: load the reference's pk.bin next to a
+        constraint-system-only blob (circuits.Circuit.cs_blob)"""
         self.params = params
         h = C.c_uint64(0)
         blob = bytes(circuit_blob)
-        _chk(lib().zkgpu_pk_create(C.c_uint64(params.handle), blob, C.c_size_t(len(blob)), C.byref(h)))
+        if pk_bin is None:
+            _chk(lib().zkgpu_pk_create(C.c_uint64(params.handle), blob, C.c_size_t(len(blob)), C.byref(h)))
+        else:
+            pk_bin = bytes(pk_bin)
+            _chk(lib().zkgpu_pk_load(C.c_uint64(params.handle), blob, C.c_size_t(len(blob)), pk_bin, C.c_size_t(len(pk_bin)), C.byref(h)))
         self.handle = h.value
         info = np.zeros(16, dtype=np.uint64)
         _chk(lib().zkgpu_pk_info(C.c_uint64(self.handle), _p(info)))

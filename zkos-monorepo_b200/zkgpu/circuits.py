@@ -18,6 +18,7 @@ import numpy as np
 OP_CONST, OP_FIXED, OP_ADVICE, OP_INSTANCE, OP_NEG, OP_ADD, OP_MUL, OP_SCALE = range(8)
 COL_ADVICE, COL_FIXED, COL_INSTANCE = 0, 1, 2
 MAGIC = 0x5A4B4353
+CS_ONLY_MAGIC = 0x5A4B4354   # constraint system only: what the Rust exporter of INTEGRATION.md writes next to a pk.bin
 
 # name -> (k, arithmetic units, pow5 units, public inputs)   (public-input counts: SURVEY §8d config 5;
 # /root/reference/contracts/Shielder.sol:504-519, 679-701)
@@ -168,9 +169,14 @@ class Circuit:
         self.copies = copies
         self.blob = self._serialize()
 
-    def _serialize(self):
+    def cs_blob(self, transcript_repr, num_selectors=0):
+        """The constraint system alone (no fixed assignment, no copy constraints — a pk.bin holds what is derived from those), followed by
+        the number of selector bit-vectors in the pk.bin's verifying-key section and `vk.transcript_repr()` (4 Montgomery limbs)."""
+        return self._serialize(cs_only=(np.ascontiguousarray(transcript_repr, dtype=np.uint64), num_selectors))
+
+    def _serialize(self, cs_only=None):
         s = self.shape
-        out = [struct.pack("<5I", MAGIC, s.k, s.num_fixed, s.num_advice, 1)]
+        out = [struct.pack("<5I", CS_ONLY_MAGIC if cs_only else MAGIC, s.k, s.num_fixed, s.num_advice, 1)]
         for qs in (s.advice_queries, s.fixed_queries, s.instance_queries):
             out.append(struct.pack("<I", len(qs)))
             for c, r in qs:
@@ -192,6 +198,10 @@ class Circuit:
                 for e in exprs:
                     out.append(struct.pack("<I", len(e)))
                     out.append(np.array(e, dtype=np.uint32).tobytes())
+        if cs_only:
+            out.append(struct.pack("<I", cs_only[1]))
+            out.append(cs_only[0].tobytes())
+            return b"".join(out)
         out.append(np.ascontiguousarray(self.fixed).tobytes())
         out.append(struct.pack("<I", len(self.copies)))
         out.append(np.array(self.copies, dtype=np.uint32).tobytes())
