@@ -58,6 +58,11 @@ const char* zkgpu_last_error(void);
 /* ABI version of this header (bumped on any signature change). */
 int zkgpu_abi_version(void);
 
+/* Keccak-256 with the EVM's padding: the hash behind the Keccak256 transcript (known answers at
+ * /root/reference/crates/shielder-account/src/secrets.rs:75-106) and behind the contract-side `commitment` public inputs
+ * (/root/reference/contracts/Shielder.sol:351-356).  Host only, needs no GPU. */
+int zkgpu_keccak256(const uint8_t* data, size_t len, uint8_t out[32]);
+
 /* ---- MSM: halo2curves::msm::best_multiexp(coeffs, bases) -> G1 -------------------------------- */
 int zkgpu_msm_g1(const uint64_t* scalars, const uint64_t* bases_affine, size_t n, uint64_t out_jacobian[12]);
 

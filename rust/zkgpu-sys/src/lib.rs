@@ -14,6 +14,7 @@ extern "C" {
     pub fn zkgpu_shutdown();
     pub fn zkgpu_last_error() -> *const c_char;
     pub fn zkgpu_abi_version() -> c_int;
+    pub fn zkgpu_keccak256(data: *const u8, len: usize, out: *mut u8) -> c_int;
 
     pub fn zkgpu_msm_g1(scalars: *const u64, bases_affine: *const u64, n: usize, out_jacobian: *mut u64) -> c_int;
     pub fn zkgpu_srs_register(g: *const u64, g_lagrange: *const u64, k: u32, handle_out: *mut u64) -> c_int;

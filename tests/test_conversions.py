@@ -30,10 +30,11 @@ def test_hex_and_u256_and_bytes():
     assert cv.hex_to_u256(HEX_41) == 41
     assert np.array_equal(cv.hex_32_to_f(HEX_41), cv.fr(41))
     assert cv.bytes_to_u256(BYTES_41) == 41 and cv.u256_to_bytes(41) == BYTES_41
-    with pytest.raises(cv.HexU256ParseError):
-        cv.hex_to_u256("29")
-    with pytest.raises(cv.HexU256ParseError):
-        cv.hex_to_u256("0xzz")
+    # `U256::from_str` (ruint) also reads un-prefixed decimal and 0o / 0b prefixes
+    assert cv.hex_to_u256("29") == 29 and cv.hex_to_u256("0o51") == 41 and cv.hex_to_u256("0b101001") == 41 and cv.hex_to_u256("0X29") == 41
+    for bad in ("0xzz", "", "0x", "-1", "4 1", "0x" + "1" + "0" * 64):
+        with pytest.raises(cv.HexU256ParseError):
+            cv.hex_to_u256(bad)
 
 
 def test_between_address_and_field():
@@ -91,3 +92,31 @@ def test_encode_calldata():
     # unaligned proofs are zero-padded to a word boundary
     cd2 = cv.encode_calldata(b"\x01\x02\x03", [])
     assert len(cd2) == 4 + 32 * 5 and cd2[4 + 96: 4 + 128] == b"\x01\x02\x03" + bytes(29)
+
+
+def test_serialize_public_input_orders_follow_the_contract():
+    """instance-column order = the order Shielder.sol feeds the verifier (contracts/Shielder.sol:347-370, 505-519, 680-701)"""
+    w = {k: cv.field_to_bytes(cv.fr(10 + i)) for i, k in enumerate(
+        ["merkle_root", "h_nullifier_old", "h_note_new", "withdrawal_value", "token_address", "commitment", "mac_salt", "mac_commitment"])}
+    inst = cv.serialize_public_input("withdraw", w)
+    assert inst.shape == (8, 4) and [cv.fr_value(x) for x in inst] == list(range(10, 18))
+    d = dict(w); d["value"] = d.pop("withdrawal_value")
+    got = [cv.fr_value(x) for x in cv.serialize_public_input("deposit", d)]
+    assert got == [10, 11, 12, 13, 15, 14, 16, 17]          # deposit: commitment BEFORE token_address
+    assert len(cv.INSTANCE_ORDER["new_account"]) == 13
+    with pytest.raises(KeyError):
+        cv.serialize_public_input("withdraw", d)
+    bad = dict(w); bad["mac_salt"] = b"\xff" * 32            # not a canonical field element
+    with pytest.raises(Exception):
+        cv.serialize_public_input("withdraw", bad)
+
+
+def test_commitment_word_and_keccak_known_answer():
+    """zkgpu_keccak256 needs no GPU: the reference's own known answer (crates/shielder-account/src/secrets.rs:75-92), and the
+    `>> 4` the contract applies so that the commitment is below r"""
+    import zkgpu
+    m1 = (15).to_bytes(32, "big") + b"nullifier" + (0xFF).to_bytes(4, "big")
+    assert zkgpu._keccak256(m1).hex() == "375a07a9503d15a291307e33ad0c297c9768fea4712947172ad09f2df34d8015"
+    word = cv.commitment_word(m1)
+    assert int.from_bytes(word, "little") == int("375a07a9503d15a291307e33ad0c297c9768fea4712947172ad09f2df34d8015", 16) >> 4
+    cv.vec_to_f(word)                                         # below r: a valid public input

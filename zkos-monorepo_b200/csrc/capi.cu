@@ -148,6 +148,15 @@ SrsEntry& Context::get_srs(uint64_t h) {
 void Context::msm_srs_dev(SrsEntry& S, int basis, const fr_t* d_scalars, size_t n, size_t m, g1_affine_t* d_out_affine, cudaStream_t st) {
     ZK_REQUIRE(basis == 0 || basis == 1, "basis must be 0 (g) or 1 (g_lagrange)");
     ZK_REQUIRE(n >= 1 && n <= S.n, "msm: n exceeds the registered SRS size");
+    if (S.lat_tables.p && m <= ZK_LAT_MAX_M) {
+        // one or a few commitments per call (what `ParamsKZG::commit{,_lagrange}` issues one at a time): the latency path
+        MsmPlan lp = S.lat_plan;
+        lp.n = n; lp.tstride = S.n;
+        const fr_t* sc[ZK_LAT_MAX_M];
+        for (size_t i = 0; i < m; ++i) sc[i] = d_scalars + i * n;
+        msm_lat_run(lp, sc, basis ? ~0u : 0u, S.lat_stride(), S.lat_tables.p, m, d_out_affine, ws, st);
+        return;
+    }
     MsmPlan plan = S.plan;
     plan.n = n; plan.tstride = S.n;
     const size_t chunk = 1024;
@@ -177,6 +186,12 @@ using namespace zk;
 extern "C" {
 
 int zkgpu_abi_version(void) { return 3; }
+/* Keccak-256 (EVM padding): the hash of the Keccak256 transcript and of the contract-side `commitment` public inputs; host only */
+int zkgpu_keccak256(const uint8_t* data, size_t len, uint8_t out[32]) {
+    if ((!data && len) || !out) { g_last_error = "null pointer"; return ZKGPU_ERR_ARG; }
+    keccak256(data ? data : reinterpret_cast<const uint8_t*>(""), len, out);
+    return ZKGPU_OK;
+}
 const char* zkgpu_last_error(void) { return g_last_error.c_str(); }
 uint64_t zkgpu_launch_count(void) { return g_launches.load(); }
 
@@ -252,7 +267,17 @@ int zkgpu_srs_register(const uint64_t* g, const uint64_t* g_lagrange, uint32_t k
             ZK_CUDA(cudaMemcpyAsync(C.pt_buf.p, src[b], S->n * 64, cudaMemcpyHostToDevice, st));
             msm_precompute_table(S->plan, C.pt_buf.p, S->table[b].p, st);
         }
-        ZK_CUDA(cudaStreamSynchronize(st));
+        // narrow-window tables of both bases, back to back, for the latency path (a few MSMs per launch group: single proofs)
+        if (msm_lat_window()) {
+            S->lat_plan = msm_plan(S->n, true, msm_lat_window());
+            S->lat_plan.tstride = S->n;
+            S->lat_tables.alloc(2 * S->n * S->lat_plan.W);
+            for (int b = 0; b < 2; ++b) {
+                ZK_CUDA(cudaMemcpyAsync(C.pt_buf.p, src[b], S->n * 64, cudaMemcpyHostToDevice, st));
+                msm_precompute_table(S->lat_plan, C.pt_buf.p, S->lat_tables.p + (size_t)b * S->n * S->lat_plan.W, st);
+            }
+            ZK_CUDA(cudaStreamSynchronize(st));
+        }
         std::unique_lock<std::shared_mutex> tl(R.tab_mu);
         C.srs[h] = std::move(S);
     }

@@ -25,7 +25,8 @@ struct SrsEntry {
     // latency plan: a second, narrow-window table for launch groups of a few MSMs (single proofs), where the bucket
     // reduction's dependent chain — not the number of additions — is what takes the time
     MsmPlan lat_plan;
-    DevBuf<g1_affine_t> lat_table[2];
+    DevBuf<g1_affine_t> lat_tables;   // [2][W_lat][n]: g, then g_lagrange
+    size_t lat_stride() const { return n * lat_plan.W; }
 };
 
 struct Context {

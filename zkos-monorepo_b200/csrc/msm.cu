@@ -564,6 +564,198 @@ __global__ void k_msm_reduce_fold(const g1_xyzz_t* __restrict__ partial, g1_xyzz
     xyzz_store(groups + g, acc);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Latency path: a handful of fixed-base MSMs (the commitments of ONE proof).
+// The throughput kernels above give every bucket one thread and every bucket group one CTA; with a few MSMs in flight that is a
+// few long dependent chains on an otherwise idle GPU (round 1: 6 commitment rounds x ~1 ms of a 6.4 ms proof).  Here the SRS
+// carries a second, NARROW-window table (c = 10: 512 buckets, 26 windows), so that
+//   * every bucket holds hundreds of points and is accumulated by TPB threads (strided slices + a shared-memory tree), and
+//   * the bucket reduction  sum_b (b+1) B_b = sum_b sfx[b]  (sfx = inclusive suffix sums) is ONE CTA per MSM: a suffix scan and a
+//     tree, 2 log2(nb) dependent additions instead of ~45, followed by the affine normalisation in the same kernel.
+// The digit sort aggregates its histogram in shared memory per CTA (512 counters would serialise ~400 global atomics each).
+// MSM m reads its scalars at sc[m] and its points from table + (basis bit m) * table_stride, so commitments over g and over
+// g_lagrange share one launch group.
+// ---------------------------------------------------------------------------------------------
+struct LatArgs {
+    const fr_t* sc[ZK_LAT_MAX_M];
+    uint32_t basis_mask;
+    uint32_t table_stride;   // points between the two bases' tables
+};
+
+__global__ void __launch_bounds__(256) k_lat_count(LatArgs A, MsmDims D, uint32_t* __restrict__ counts) {
+    extern __shared__ uint32_t lat_sm[];   // [nb]
+    const unsigned m = blockIdx.y;   // grid (chunks of 256 scalars, M)
+    for (unsigned b = threadIdx.x; b < D.nb; b += blockDim.x) lat_sm[b] = 0;
+    __syncthreads();
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < D.n) {
+        fr_t s = from_mont(fe_load(A.sc[m] + i));
+        for_each_digit(s.l, D.c, D.W, [&](unsigned, uint32_t mag, bool) { atomicAdd(&lat_sm[mag - 1], 1u); });
+    }
+    __syncthreads();
+    for (unsigned b = threadIdx.x; b < D.nb; b += blockDim.x)
+        if (lat_sm[b]) atomicAdd(counts + (size_t)m * D.nb + b, lat_sm[b]);
+}
+// cursors[m][b] start at offsets[m][b]; every CTA reserves a range per bucket and fills it from shared-memory counters
+__global__ void __launch_bounds__(256) k_lat_scatter(LatArgs A, MsmDims D, uint32_t* __restrict__ cursors, uint32_t* __restrict__ entries) {
+    extern __shared__ uint32_t lat_sm[];   // [nb] counts -> bases, [nb] local cursors
+    uint32_t* base = lat_sm; uint32_t* local = lat_sm + D.nb;
+    const unsigned m = blockIdx.y;
+    for (unsigned b = threadIdx.x; b < D.nb; b += blockDim.x) { base[b] = 0; local[b] = 0; }
+    __syncthreads();
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    fr_t s = fr_t::zero();
+    if (i < D.n) {
+        s = from_mont(fe_load(A.sc[m] + i));
+        for_each_digit(s.l, D.c, D.W, [&](unsigned, uint32_t mag, bool) { atomicAdd(&base[mag - 1], 1u); });
+    }
+    __syncthreads();
+    for (unsigned b = threadIdx.x; b < D.nb; b += blockDim.x)
+        if (base[b]) base[b] = atomicAdd(cursors + (size_t)m * (D.nb + 1) + b, base[b]);
+    __syncthreads();
+    if (i < D.n) {
+        uint32_t* em = entries + (size_t)m * ((size_t)D.n * D.W);
+        const uint32_t tb = ((A.basis_mask >> m) & 1u) * A.table_stride;
+        for_each_digit(s.l, D.c, D.W, [&](unsigned w, uint32_t mag, bool negative) {
+            uint32_t pos = base[mag - 1] + atomicAdd(&local[mag - 1], 1u);
+            em[pos] = (tb + w * D.tstride + i) | (negative ? 0x80000000u : 0u);
+        });
+    }
+}
+__global__ void k_lat_init_cursors(const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursors, size_t total) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < total) cursors[t] = offsets[t];
+}
+
+// TPB threads per bucket, 128 / TPB buckets per CTA
+#define ZK_LAT_HEAVY_PER_THREAD 48   // a bucket with more entries per thread than this goes to k_lat_heavy (512 threads per bucket)
+template <unsigned TPB>
+__global__ void __launch_bounds__(128) k_lat_buckets(const g1_affine_t* __restrict__ table, const uint32_t* __restrict__ offsets,
+                                                     const uint32_t* __restrict__ entries, MsmDims D, size_t M, g1_xyzz_t* __restrict__ buckets,
+                                                     uint32_t* __restrict__ heavy_count, uint64_t* __restrict__ heavy_list) {
+    __shared__ g1_xyzz_t part[128];
+    const unsigned lane = threadIdx.x % TPB;
+    const size_t idx = ((size_t)blockIdx.x * 128 + threadIdx.x) / TPB;   // (m, bucket)
+    bool live = idx < M * D.nb;
+    g1_xyzz_t acc = g1_xyzz_t::identity();
+    if (live) {
+        const size_t m = idx / D.nb, key = idx - m * D.nb;
+        const uint32_t* om = offsets + m * ((size_t)D.nb + 1);
+        const uint32_t* em = entries + m * ((size_t)D.n * D.W);
+        const uint32_t b = om[key], e = om[key + 1];
+        const uint32_t heavy = D.heavy > ZK_LAT_HEAVY_PER_THREAD * TPB ? D.heavy : ZK_LAT_HEAVY_PER_THREAD * TPB;   // D.heavy: 4x the mean run
+        if (e - b > heavy) {   // skewed scalars (a constant column puts all n points of a window in one bucket)
+            if (lane == 0) heavy_list[atomicAdd(heavy_count, 1u)] = idx;
+            live = false;
+        } else
+        for (uint32_t t = b + lane; t < e; t += TPB) {
+            const uint32_t ref = em[t];
+            const g1_affine_t* p = table + (ref & 0x7fffffffu);
+            g1_affine_t q;
+            q.x = fe_ldg(&p->x); q.y = fe_ldg(&p->y);
+            xyzz_madd(acc, q, (ref >> 31) != 0);
+        }
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (unsigned s2 = TPB >> 1; s2 > 0; s2 >>= 1) {
+        if (lane < s2) part[threadIdx.x] = xyzz_add(part[threadIdx.x], part[threadIdx.x + s2]);
+        __syncthreads();
+    }
+    if (live && lane == 0) xyzz_store(buckets + idx, part[threadIdx.x]);
+}
+
+// heavy buckets of the latency path: one CTA of 512 threads per bucket (grid-stride over the worklist)
+__global__ void __launch_bounds__(512) k_lat_heavy(const g1_affine_t* __restrict__ table, const uint32_t* __restrict__ offsets,
+                                                   const uint32_t* __restrict__ entries, MsmDims D, g1_xyzz_t* __restrict__ buckets,
+                                                   const uint32_t* __restrict__ heavy_count, const uint64_t* __restrict__ heavy_list) {
+    extern __shared__ uint4 lat_heavy_sm[];
+    g1_xyzz_t* part = reinterpret_cast<g1_xyzz_t*>(lat_heavy_sm);
+    const uint32_t count = *heavy_count;
+    for (uint32_t h = blockIdx.x; h < count; h += gridDim.x) {
+        const size_t idx = heavy_list[h];
+        const size_t m = idx / D.nb, key = idx - m * D.nb;
+        const uint32_t* om = offsets + m * ((size_t)D.nb + 1);
+        const uint32_t* em = entries + m * ((size_t)D.n * D.W);
+        const uint32_t b = om[key], e = om[key + 1];
+        g1_xyzz_t acc = g1_xyzz_t::identity();
+        for (uint32_t t = b + threadIdx.x; t < e; t += blockDim.x) {
+            const uint32_t ref = em[t];
+            const g1_affine_t* p = table + (ref & 0x7fffffffu);
+            g1_affine_t q;
+            q.x = fe_ldg(&p->x); q.y = fe_ldg(&p->y);
+            xyzz_madd(acc, q, (ref >> 31) != 0);
+        }
+        part[threadIdx.x] = acc;
+        __syncthreads();
+        for (unsigned s2 = blockDim.x >> 1; s2 > 0; s2 >>= 1) {
+            if (threadIdx.x < s2) part[threadIdx.x] = xyzz_add(part[threadIdx.x], part[threadIdx.x + s2]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) xyzz_store(buckets + idx, part[0]);
+        __syncthreads();
+    }
+}
+
+// Bucket reduction of the latency path, two levels so that no SM has to push hundreds of point additions through its own
+// IMAD pipe (one 512-thread CTA per MSM took 265 us, pipe-bound on a single SM):
+//   A  one WARP per 32 consecutive buckets (grid: nb/32 x M): S = sum B, V = sum (lane+1) B as the sum of the inclusive suffix sums
+//   B  one small CTA per MSM over the nb/32 pairs: total = sum_j V_j + 32 sum_j j S_j, the second sum again as suffix sums of S;
+//      then the affine normalisation
+__global__ void __launch_bounds__(32) k_lat_reduce_a(const g1_xyzz_t* __restrict__ buckets, MsmDims D, g1_xyzz_t* __restrict__ pairs) {
+    __shared__ g1_xyzz_t part[32];
+    const unsigned t = threadIdx.x, chunk = blockIdx.x, m = blockIdx.y;
+    g1_xyzz_t v = xyzz_load(buckets + (size_t)m * D.nb + chunk * 32 + t);
+    part[t] = v;
+    __syncwarp();
+    for (unsigned d = 1; d < 32; d <<= 1) {
+        const bool has = t + d < 32;
+        g1_xyzz_t other;
+        if (has) other = part[t + d];
+        __syncwarp();
+        if (has) { v = xyzz_add(v, other); part[t] = v; }
+        __syncwarp();
+    }
+    g1_xyzz_t* out = pairs + ((size_t)m * (D.nb / 32) + chunk) * 2;
+    if (t == 0) xyzz_store(out, v);   // S: sfx[0]
+    for (unsigned s2 = 16; s2 > 0; s2 >>= 1) {
+        if (t < s2) part[t] = xyzz_add(part[t], part[t + s2]);
+        __syncwarp();
+    }
+    if (t == 0) xyzz_store(out + 1, part[0]);
+}
+__global__ void __launch_bounds__(32) k_lat_reduce_b(const g1_xyzz_t* __restrict__ pairs, MsmDims D, g1_affine_t* __restrict__ out) {
+    __shared__ g1_xyzz_t part[32];
+    const unsigned T = D.nb / 32, t = threadIdx.x;   // T <= 16 pairs; blockDim = 32, lanes >= T idle
+    const g1_xyzz_t* pr = pairs + (size_t)blockIdx.x * T * 2;
+    g1_xyzz_t s = t < T ? xyzz_load(pr + 2 * t) : g1_xyzz_t::identity();
+    part[t] = s;
+    __syncwarp();
+    for (unsigned d = 1; d < T; d <<= 1) {
+        const bool has = t + d < T;
+        g1_xyzz_t other;
+        if (has) other = part[t + d];
+        __syncwarp();
+        if (has) { s = xyzz_add(s, other); part[t] = s; }
+        __syncwarp();
+    }
+    g1_xyzz_t v = t < T ? xyzz_load(pr + 2 * t + 1) : g1_xyzz_t::identity();
+    if (t >= 1 && t < T) {
+        for (unsigned l = 1; l < 32; l <<= 1) s = xyzz_dbl(s);   // 32 * sfxS[t]
+        v = xyzz_add(v, s);
+    }
+    part[t] = v;
+    __syncwarp();
+    for (unsigned s2 = 16; s2 > 0; s2 >>= 1) {
+        if (t < s2) part[t] = xyzz_add(part[t], part[t + s2]);
+        __syncwarp();
+    }
+    if (t == 0) {
+        g1_affine_t a = xyzz_to_affine(part[0]);
+        fe_store(&out[blockIdx.x].x, a.x); fe_store(&out[blockIdx.x].y, a.y);
+    }
+}
+
 __global__ void k_msm_combine(const g1_xyzz_t* __restrict__ groups, MsmDims D, size_t M, g1_xyzz_t* __restrict__ out) {
     size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
@@ -627,7 +819,7 @@ void MsmWorkspace::ensure(const MsmPlan& p, size_t M) {
     entries.ensure(M * p.entries_per_msm());
     buckets.ensure(M * K);
     groups.ensure(M * p.G);
-    order.ensure(M * K);
+    order.ensure(M * (K + 1));   // M * K bucket ranks; the latency path keeps its (K + 1)-strided scatter cursors here
     heavy_count.ensure(1);
     heavy_list.ensure(M * p.entries_per_msm() / ZK_HEAVY_MIN + 1);
 }
@@ -719,6 +911,57 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
     if (!plan.precomp) {
         ZK_LAUNCH(k_msm_combine, ceil_div(M, 64), 64, 0, st, ws.groups.p, D, M, d_out);
     }
+}
+
+unsigned msm_lat_window() {
+    static const unsigned c = [] { const char* e = getenv("ZKGPU_LAT_C"); int v = e ? atoi(e) : 10; return (unsigned)((v >= 6 && v <= 10) ? v : v == 0 ? 0 : 10); }();
+    return c;
+}
+
+void msm_lat_run(const MsmPlan& plan, const fr_t* const* d_scalars, uint32_t basis_mask, size_t table_stride, const g1_affine_t* d_tables,
+                 size_t M, g1_affine_t* d_out_affine, MsmWorkspace& ws, cudaStream_t st) {
+    if (M == 0) return;
+    ZK_REQUIRE(M <= ZK_LAT_MAX_M && plan.precomp && plan.nb <= 512 && plan.nb >= 32, "msm_lat_run: unsupported shape");
+    ws.ensure(plan, M);
+    MsmDims D = dims_of(plan);
+    LatArgs A;
+    for (size_t m = 0; m < ZK_LAT_MAX_M; ++m) A.sc[m] = d_scalars[m < M ? m : 0];
+    A.basis_mask = basis_mask; A.table_stride = (uint32_t)table_stride;
+    ZK_REQUIRE(2 * table_stride < (1ull << 31), "msm_lat_run: table too large for 31-bit entries");
+    const size_t K = plan.nb;
+    const dim3 grid(ceil_div(plan.n, 256), (unsigned)M);
+    {
+        KtScope kt(KT_MSM_SORT, st);
+        ZK_CUDA(cudaMemsetAsync(ws.counts.p, 0, M * K * sizeof(uint32_t), st));
+        ZK_LAUNCH(k_lat_count, grid, 256, K * sizeof(uint32_t), st, A, D, ws.counts.p);
+        unsigned scan_threads = 32;
+        while (scan_threads < K && scan_threads < 1024) scan_threads <<= 1;
+        ZK_LAUNCH(k_msm_scan, (unsigned)M, scan_threads, 0, st, ws.counts.p, ws.offsets.p, (unsigned)K);
+        // the (K+1)-strided cursor array lives in `order` (unused by this path)
+        ZK_LAUNCH(k_lat_init_cursors, ceil_div(M * (K + 1), 256), 256, 0, st, ws.offsets.p, ws.order.p, M * (K + 1));
+        ZK_LAUNCH(k_lat_scatter, grid, 256, 2 * K * sizeof(uint32_t), st, A, D, ws.order.p, ws.entries.p);
+    }
+    {
+        KtScope kt(KT_MSM_BUCKETS, st);
+        ZK_CUDA(cudaMemsetAsync(ws.heavy_count.p, 0, sizeof(uint32_t), st));
+        // threads per bucket: as few as still give every SM ~16 warps (the additions of a thread are dependent; the fold across the
+        // TPB threads of a bucket costs log2 TPB more), at most 128 (one CTA per bucket)
+        const size_t nbk = M * K;
+        const size_t fill = (size_t)148 * 512;
+#define ZK_LAT_BUCKETS(TPB) ZK_LAUNCH(k_lat_buckets<TPB>, ceil_div(nbk * TPB, 128), 128, 0, st, d_tables, ws.offsets.p, ws.entries.p, D, M, ws.buckets.p, \
+                                      ws.heavy_count.p, ws.heavy_list.p)
+        if (nbk * 8 >= fill) ZK_LAT_BUCKETS(8);
+        else if (nbk * 32 >= fill) ZK_LAT_BUCKETS(32);
+        else ZK_LAT_BUCKETS(128);
+#undef ZK_LAT_BUCKETS
+        static DeviceOnce once;
+        once.run([] { ZK_CUDA(cudaFuncSetAttribute(k_lat_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * (int)sizeof(g1_xyzz_t))); });
+        ZK_LAUNCH(k_lat_heavy, 128, 512, 512 * sizeof(g1_xyzz_t), st, d_tables, ws.offsets.p, ws.entries.p, D, ws.buckets.p, ws.heavy_count.p, ws.heavy_list.p);
+    }
+    KtScope kt(KT_MSM_REDUCE, st);
+    ws.partial.ensure(M * (K / 32) * 2);
+    ZK_LAUNCH(k_lat_reduce_a, dim3((unsigned)(K / 32), (unsigned)M), 32, 0, st, ws.buckets.p, D, ws.partial.p);
+    ZK_LAUNCH(k_lat_reduce_b, (unsigned)M, 32, 0, st, ws.partial.p, D, d_out_affine);
 }
 
 void msm_precompute_table(const MsmPlan& plan, const g1_affine_t* d_bases, g1_affine_t* d_table, cudaStream_t st) {

@@ -37,6 +37,13 @@ struct MsmWorkspace {
 // out[m] = sum_i scalars[m*n + i] * bases[i]  (XYZZ, not normalised).  Scalars in Montgomery form.
 void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_bases_or_table, size_t M,
              g1_xyzz_t* d_out, MsmWorkspace& ws, cudaStream_t st);
+// Latency path for M <= ZK_LAT_MAX_M fixed-base MSMs over a narrow-window table (`plan` from msm_plan(n, true, c_lat)): MSM m reads
+// n scalars at d_scalars[m] (host array of device pointers) and points from d_tables + (bit m of basis_mask) * table_stride.
+// Affine results (normalised) in d_out_affine[m].
+#define ZK_LAT_MAX_M 32
+unsigned msm_lat_window();   // window width of the latency tables (ZKGPU_LAT_C, default 10; 0 disables the latency path)
+void msm_lat_run(const MsmPlan& plan, const fr_t* const* d_scalars, uint32_t basis_mask, size_t table_stride, const g1_affine_t* d_tables,
+                 size_t M, g1_affine_t* d_out_affine, MsmWorkspace& ws, cudaStream_t st);
 // table[w*n + i] = 2^(c*w) * bases[i], affine
 void msm_precompute_table(const MsmPlan& plan, const g1_affine_t* d_bases, g1_affine_t* d_table, cudaStream_t st);
 // affine normalisation of m points (one inversion each)

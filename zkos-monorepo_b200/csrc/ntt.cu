@@ -353,7 +353,7 @@ static unsigned pick_swz(unsigned log_m, unsigned log_C) {
 
 // 2^13 (Shielder's MAX_K) runs as one launch of two-CTA clusters when there are enough polynomials to give every SM a CTA
 // (measured, profiles/r02_ab_bench.md: 235.7 -> 230.4 ms per 1024 proofs; for the few transforms of a single proof the two-pass
-// path has more CTAs in flight and is faster).  ZKGPU_NTT_CLUSTER=0 falls back to the two-pass path everywhere.
+// path has more CTAs in flight and is faster: 120 polynomials take 175 us as clusters, 72 us as two passes).  ZKGPU_NTT_CLUSTER=0 falls back to the two-pass path everywhere.
 static bool ntt_use_cluster() {
     static const bool on = [] { const char* e = getenv("ZKGPU_NTT_CLUSTER"); return e ? atoi(e) != 0 : true; }();
     return on;

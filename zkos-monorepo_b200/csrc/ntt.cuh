@@ -8,7 +8,7 @@ namespace zk {
 
 static const unsigned NTT_SINGLE_PASS_MAX_LOG = 12;  // 2^12 * 32 B = 128 KB of shared memory
 static const unsigned NTT_CLUSTER_LOG = 13;          // 2^13: one launch of two-CTA clusters (distributed shared memory)
-static const size_t NTT_CLUSTER_MIN_BATCH = 74;      // ... from 74 polynomials on (148 SMs, one CTA of the pair each)
+static const size_t NTT_CLUSTER_MIN_BATCH = 592;     // ... from 592 polynomials on (148 SMs x 8 CTAs of a pair: several full waves)
 
 struct NttJob {
     const fr_t* in = nullptr;   // batch polynomials, stride in_stride (0 = N)

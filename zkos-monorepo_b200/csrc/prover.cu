@@ -162,7 +162,7 @@ struct ProverWs {
 };
 
 static const unsigned BATCH_WORKERS = 3;   // pipeline workers of a zkgpu_prove_batch call
-static const unsigned COALESCE_WORKERS = 2;   // dispatcher threads (per device) behind zkgpu_prove
+static const unsigned COALESCE_WORKERS = 3;   // dispatcher threads (per device) behind zkgpu_prove: one uploads while two compute
 struct PkEntry {   // one replica per selected device
     Context* C = nullptr;
     std::mutex batch_mu;   // one zkgpu_prove_batch at a time per replica (its workers own ws[0..2])
@@ -283,10 +283,34 @@ static void coset_ext(PkEntry& pk, ProverWs& W, const fr_t* in, fr_t* out, size_
         ntt_run(J, st);
     }
 }
+// A few commitments (the rounds of a single proof): the latency path of msm.cu over the SRS's narrow-window tables; every item names its
+// basis (0 = g, 1 = g_lagrange), so the commitments of one Fiat-Shamir round share a launch group whatever their basis.
+struct CommitItem { int basis; const fr_t* scalars; };
+static bool commit_lat_ok(Context& C, const PkEntry& pk, size_t M) {
+    SrsEntry& S = C.get_srs(pk.srs_handle);
+    return S.lat_tables.p != nullptr && M >= 1 && M <= ZK_LAT_MAX_M;
+}
+static void commit_lat(Context& C, PkEntry& pk, ProverWs& W, const std::vector<CommitItem>& items, g1_affine_t* d_out, cudaStream_t st) {
+    SrsEntry& S = C.get_srs(pk.srs_handle);
+    MsmPlan plan = S.lat_plan;
+    plan.n = pk.n; plan.tstride = S.n;
+    const fr_t* sc[ZK_LAT_MAX_M];
+    uint32_t mask = 0;
+    for (size_t m = 0; m < items.size(); ++m) { sc[m] = items[m].scalars; if (items[m].basis) mask |= 1u << m; }
+    msm_lat_run(plan, sc, mask, S.lat_stride(), S.lat_tables.p, items.size(), d_out, W.msm, st);
+}
+
 // M commitments; MSM m reads scalars at (m / inner) * outer_stride + (m % inner) * n.  Affine out.
 static void commit(Context& C, PkEntry& pk, ProverWs& W, int basis, const fr_t* d_scalars, size_t M, size_t inner, size_t outer_stride,
                    g1_affine_t* d_out, cudaStream_t st) {
     SrsEntry& S = C.get_srs(pk.srs_handle);
+    if (commit_lat_ok(C, pk, M)) {
+        std::vector<CommitItem> items(M);
+        for (size_t m = 0; m < M; ++m)
+            items[m] = {basis, inner ? d_scalars + (m / inner) * outer_stride + (m % inner) * pk.n : d_scalars + m * pk.n};
+        commit_lat(C, pk, W, items, d_out, st);
+        return;
+    }
     MsmPlan plan = S.plan;
     plan.n = pk.n; plan.tstride = S.n;
     if (inner == 0) { inner = 1; outer_stride = pk.n; }
@@ -791,10 +815,7 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
         W.carries.ensure(B * P);
         launch_perm_finalize(W.z.p, W.carries.p, pk.k, pk.P, pk.bf, W.raw_z.p, B, st);
     }
-    if (P) {
-        trace_dev("z", W.z.p, n, P, n, st);
-        commit(C, pk, W, 1, W.z.p, B * P, 0, 0, W.aff.p, st);
-    }
+    if (P) trace_dev("z", W.z.p, n, P, n, st);
     if (L) {
         // lookup arguments, part 2: grand products
         fr_t* num = W.adv_ext.p + 2 * B * P * n; fr_t* den = num + B * L * n;
@@ -806,11 +827,21 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
             launch_perm_finalize(W.lk_z.p, W.carries.p, pk.k, 1, pk.bf, W.raw_lz.p, B * L, st);
         }
         trace_dev("lookup_z", W.lk_z.p, n, L, n, st);
-        commit(C, pk, W, 1, W.lk_z.p, B * L, 0, 0, W.aff.p + B * P, st);
     }
     launch_chacha_poly(W.seeds.p, W.randp.p, n, B, vchunk, vnch, st);
     trace_dev("random_poly", W.randp.p, n, 1, n, st);
-    commit(C, pk, W, 0, W.randp.p, B, 0, 0, W.aff.p + B * (P + L), st);
+    // the round's commitments: permutation products, lookup products (both over g_lagrange) and the random polynomial (over g)
+    if (commit_lat_ok(C, pk, B * (P + L + 1))) {
+        std::vector<CommitItem> items;
+        for (size_t i = 0; i < B * P; ++i) items.push_back({1, W.z.p + i * n});
+        for (size_t i = 0; i < B * L; ++i) items.push_back({1, W.lk_z.p + i * n});
+        for (size_t b = 0; b < B; ++b) items.push_back({0, W.randp.p + b * n});
+        commit_lat(C, pk, W, items, W.aff.p, st);
+    } else {
+        if (P) commit(C, pk, W, 1, W.z.p, B * P, 0, 0, W.aff.p, st);
+        if (L) commit(C, pk, W, 1, W.lk_z.p, B * L, 0, 0, W.aff.p + B * P, st);
+        commit(C, pk, W, 0, W.randp.p, B, 0, 0, W.aff.p + B * (P + L), st);
+    }
     ZK_CUDA(cudaMemcpyAsync(W.h_aff.p, W.aff.p, B * (P + L + 1) * sizeof(g1_affine_t), cudaMemcpyDeviceToHost, st));
     if (!W.ev_pts) ZK_CUDA(cudaEventCreateWithFlags(&W.ev_pts, cudaEventDisableTiming));
     cudaEvent_t ev_pts = W.ev_pts;

@@ -72,6 +72,12 @@ def launch_count():
     return int(lib().zkgpu_launch_count())
 
 
+def _keccak256(data):
+    out = C.create_string_buffer(32)
+    _chk(lib().zkgpu_keccak256(bytes(data), C.c_size_t(len(data)), out))
+    return out.raw
+
+
 def _jac_to_affine(j):
     """normalised Jacobian (x, y, 1) / (0, 1, 0) -> affine (x, y) / (0, 0)"""
     out = np.zeros(8, dtype=np.uint64)

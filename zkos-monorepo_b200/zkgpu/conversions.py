@@ -87,11 +87,14 @@ def field_to_bytes(f):
 
 
 def hex_to_u256(text):
-    """lib.rs:82-84 — hex string with 0x prefix"""
+    """lib.rs:82-84 — `U256::from_str` (ruint): 0x / 0X hex, 0o octal, 0b binary prefixes, otherwise decimal digits"""
     try:
-        if not text.startswith("0x"):
+        low = text[:2].lower()
+        radix = {"0x": 16, "0o": 8, "0b": 2}.get(low, 10)
+        digits = text[2:] if radix != 10 else text
+        if not digits or digits[0] in "+-_" or "_" in digits or not digits.isascii():
             raise ValueError
-        v = int(text[2:], 16)
+        v = int(digits, radix)
     except ValueError:
         raise HexU256ParseError()
     if v >= 1 << 256:
@@ -159,6 +162,39 @@ def vec_to_path(v):
             o = (i * ARITY + j) * FR_SIZE
             out[i, j] = bytes_to_field(v[o:o + FR_SIZE])
     return out
+
+
+# ---- serialize_public_input: the instance column of a proof from the bindings' public-input byte structs -----------
+# Field names: `NewAccountPubInputsBytes` / `DepositPubInputsBytes` / `WithdrawPubInputsBytes`
+# (/root/reference/crates/shielder_bindings/src/circuits/{new_account.rs:19-33, deposit.rs:18-27, withdraw.rs:18-27}); the ORDER of the
+# instance column ("needs to match the order in the circuit") is the one the contract feeds the verifier:
+# /root/reference/contracts/Shielder.sol:347-370 (13 inputs), :505-519 (8), :680-701 (8).
+INSTANCE_ORDER = {
+    "new_account": ("hashed_note", "prenullifier", "initial_deposit", "commitment", "token_address", "anonymity_revoker_public_key_x",
+                    "anonymity_revoker_public_key_y", "sym_key_encryption_1_x", "sym_key_encryption_1_y", "sym_key_encryption_2_x",
+                    "sym_key_encryption_2_y", "mac_salt", "mac_commitment"),
+    "deposit": ("merkle_root", "h_nullifier_old", "h_note_new", "value", "commitment", "token_address", "mac_salt", "mac_commitment"),
+    "withdraw": ("merkle_root", "h_nullifier_old", "h_note_new", "withdrawal_value", "token_address", "commitment", "mac_salt", "mac_commitment"),
+}
+
+
+def serialize_public_input(circuit, pub_inputs):
+    """`PublicInputProvider::serialize_public_input` over the byte struct of `circuit` ("new_account" / "deposit" / "withdraw"):
+    `pub_inputs` maps the struct's field names to canonical little-endian 32-byte words; returns the (num_pi, 4) Montgomery array
+    `zkgpu_prove_batch` takes as the proof's instance column.  Missing or unknown fields and non-canonical words are errors."""
+    order = INSTANCE_ORDER[circuit]
+    extra, missing = set(pub_inputs) - set(order), [k for k in order if k not in pub_inputs]
+    if extra or missing:
+        raise KeyError("public inputs of %s: missing %s, unknown %s" % (circuit, missing, sorted(extra)))
+    return np.stack([vec_to_f(pub_inputs[k]) for k in order])
+
+
+def commitment_word(packed):
+    """the `commitment` public input: keccak256 of the abi.encodePacked call context shifted right by 4 bits so that it is below r
+    (/root/reference/contracts/Shielder.sol:351-356, 510-515, 688-699); `packed` = the abi.encodePacked bytes; returns the
+    canonical little-endian word the bindings take"""
+    from . import _keccak256
+    return (int.from_bytes(_keccak256(bytes(packed)), "big") >> 4).to_bytes(32, "little")
 
 
 # ---- calldata of the on-chain verifier -------------------------------------------------------------------
