@@ -437,12 +437,12 @@ def proofs_rooflines(env, r, steps):
     return roofline, roof_hbm, roof_imad, bound
 
 
-def timing_coverage(kt, ms_ktimed):
+def timing_coverage(kt, ms_ktimed, devices=1):
     """share of the single-worker timed step accounted for: kernel classes + the device idle time at the Fiat-Shamir round trips
     (`host_fiat_shamir_gap`: with ONE pipeline worker the GPU waits while the host hashes the transcript; the headline passes hide it
     behind the other workers' kernels).  What is left is launch gaps and the small host->device uploads."""
-    s = sum(v[0] for v in kt.values())
-    k = s - kt.get("host_fiat_shamir_gap", (0.0, 0))[0]
+    s = sum(v[0] for v in kt.values()) / devices      # the class timers add up over the devices of a single-process run
+    k = s - kt.get("host_fiat_shamir_gap", (0.0, 0))[0] / devices
     cov = s / ms_ktimed if ms_ktimed else None
     assert cov is None or cov >= 0.97, "kernel-class timers cover only %.1f %% of the timed step: a kernel is missing from the classes" % (100 * cov)
     return {"sum_of_kernel_classes_ms": round(k, 3), "host_gap_ms": round(s - k, 3), "timed_step_ms": round(ms_ktimed, 3),
@@ -665,7 +665,7 @@ def main():
                     e2e={"value": r["e2e"], "unit": UNIT, "ms_per_step": r["ms_e2e"] / args.steps, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
                     gpu_launches=r["gpu_launches"], clocks=r["clocks"], roofline=roofline, roofline_hbm=roof_hbm, roofline_imad=roof_imad, proof_bound=bound,
                     kernel_ms_per_step={k_: round(v[0], 3) for k_, v in r["ktimes"].items()}, kernel_timed_step_ms=r["ms_ktimed"],
-                    kernel_timing_coverage=timing_coverage(r["ktimes"], r["ms_ktimed"]))
+                    kernel_timing_coverage=timing_coverage(r["ktimes"], r["ms_ktimed"], env.devices))
         if "latency" in r:
             line["single_proof_p50_ms"] = r["latency"]["p50_ms"]
             line["single_proof_latency"] = r["latency"]
@@ -680,7 +680,7 @@ def main():
             line["withdraw_lookup"] = {"value": lk["value"], "unit": UNIT, "e2e": lk["e2e"], "proofs_per_step": lk["Mtot"] * env.world,
                                        "msm_per_proof": lk["shape"].num_msm, "proof_bytes": lk["pk"].proof_len,
                                        "kernel_ms_per_step": {k_: round(v[0], 3) for k_, v in lk["ktimes"].items()},
-                                       "kernel_timing_coverage": timing_coverage(lk["ktimes"], lk["ms_ktimed"]),
+                                       "kernel_timing_coverage": timing_coverage(lk["ktimes"], lk["ms_ktimed"], env.devices),
                                        "note": "64 distinct witnesses cycled over the batch (seeds distinct), 1 warm-up + 1 timed step"}
             lk["pk"].release()
             del lk

@@ -630,7 +630,7 @@ __global__ void k_lat_init_cursors(const uint32_t* __restrict__ offsets, uint32_
 // TPB threads per bucket, 128 / TPB buckets per CTA
 #define ZK_LAT_HEAVY_PER_THREAD 48   // a bucket with more entries per thread than this goes to k_lat_heavy (512 threads per bucket)
 template <unsigned TPB>
-__global__ void __launch_bounds__(128) k_lat_buckets(const g1_affine_t* __restrict__ table, const uint32_t* __restrict__ offsets,
+__global__ void __launch_bounds__(128, 4) k_lat_buckets(const g1_affine_t* __restrict__ table, const uint32_t* __restrict__ offsets,
                                                      const uint32_t* __restrict__ entries, MsmDims D, size_t M, g1_xyzz_t* __restrict__ buckets,
                                                      uint32_t* __restrict__ heavy_count, uint64_t* __restrict__ heavy_list) {
     __shared__ g1_xyzz_t part[128];
@@ -648,13 +648,13 @@ __global__ void __launch_bounds__(128) k_lat_buckets(const g1_affine_t* __restri
             if (lane == 0) heavy_list[atomicAdd(heavy_count, 1u)] = idx;
             live = false;
         } else
-        for (uint32_t t = b + lane; t < e; t += TPB) {
-            const uint32_t ref = em[t];
-            const g1_affine_t* p = table + (ref & 0x7fffffffu);
-            g1_affine_t q;
-            q.x = fe_ldg(&p->x); q.y = fe_ldg(&p->y);
-            xyzz_madd(acc, q, (ref >> 31) != 0);
-        }
+            for (uint32_t t = b + lane; t < e; t += TPB) {
+                const uint32_t ref = em[t];
+                const g1_affine_t* p = table + (ref & 0x7fffffffu);
+                g1_affine_t q;
+                q.x = fe_ldg(&p->x); q.y = fe_ldg(&p->y);
+                xyzz_madd(acc, q, (ref >> 31) != 0);
+            }
     }
     part[threadIdx.x] = acc;
     __syncthreads();
@@ -665,21 +665,26 @@ __global__ void __launch_bounds__(128) k_lat_buckets(const g1_affine_t* __restri
     if (live && lane == 0) xyzz_store(buckets + idx, part[threadIdx.x]);
 }
 
-// heavy buckets of the latency path: one CTA of 512 threads per bucket (grid-stride over the worklist)
+// heavy buckets of the latency path: ZK_LAT_HEAVY_SPLIT CTAs of 512 threads share one bucket (strided slices of its run); the last
+// CTA of a bucket to finish folds the partial sums.  `done` counts finished CTAs per heavy bucket (zeroed by the host).
+#define ZK_LAT_HEAVY_SPLIT 4
 __global__ void __launch_bounds__(512) k_lat_heavy(const g1_affine_t* __restrict__ table, const uint32_t* __restrict__ offsets,
                                                    const uint32_t* __restrict__ entries, MsmDims D, g1_xyzz_t* __restrict__ buckets,
-                                                   const uint32_t* __restrict__ heavy_count, const uint64_t* __restrict__ heavy_list) {
+                                                   const uint32_t* __restrict__ heavy_count, const uint64_t* __restrict__ heavy_list,
+                                                   g1_xyzz_t* __restrict__ partial, uint32_t* __restrict__ done) {
     extern __shared__ uint4 lat_heavy_sm[];
     g1_xyzz_t* part = reinterpret_cast<g1_xyzz_t*>(lat_heavy_sm);
+    __shared__ uint32_t last;
     const uint32_t count = *heavy_count;
-    for (uint32_t h = blockIdx.x; h < count; h += gridDim.x) {
+    const unsigned slice = blockIdx.x % ZK_LAT_HEAVY_SPLIT, stride = blockDim.x * ZK_LAT_HEAVY_SPLIT;
+    for (uint32_t h = blockIdx.x / ZK_LAT_HEAVY_SPLIT; h < count; h += gridDim.x / ZK_LAT_HEAVY_SPLIT) {
         const size_t idx = heavy_list[h];
         const size_t m = idx / D.nb, key = idx - m * D.nb;
         const uint32_t* om = offsets + m * ((size_t)D.nb + 1);
         const uint32_t* em = entries + m * ((size_t)D.n * D.W);
         const uint32_t b = om[key], e = om[key + 1];
         g1_xyzz_t acc = g1_xyzz_t::identity();
-        for (uint32_t t = b + threadIdx.x; t < e; t += blockDim.x) {
+        for (uint32_t t = b + slice * blockDim.x + threadIdx.x; t < e; t += stride) {
             const uint32_t ref = em[t];
             const g1_affine_t* p = table + (ref & 0x7fffffffu);
             g1_affine_t q;
@@ -692,7 +697,17 @@ __global__ void __launch_bounds__(512) k_lat_heavy(const g1_affine_t* __restrict
             if (threadIdx.x < s2) part[threadIdx.x] = xyzz_add(part[threadIdx.x], part[threadIdx.x + s2]);
             __syncthreads();
         }
-        if (threadIdx.x == 0) xyzz_store(buckets + idx, part[0]);
+        if (threadIdx.x == 0) {
+            xyzz_store(partial + (size_t)h * ZK_LAT_HEAVY_SPLIT + slice, part[0]);
+            __threadfence();
+            last = atomicAdd(done + h, 1u) == ZK_LAT_HEAVY_SPLIT - 1;
+            if (last) {
+                __threadfence();
+                g1_xyzz_t sum = g1_xyzz_t::identity();
+                for (unsigned j = 0; j < ZK_LAT_HEAVY_SPLIT; ++j) sum = xyzz_add(sum, xyzz_load(partial + (size_t)h * ZK_LAT_HEAVY_SPLIT + j));
+                xyzz_store(buckets + idx, sum);
+            }
+        }
         __syncthreads();
     }
 }
@@ -956,7 +971,13 @@ void msm_lat_run(const MsmPlan& plan, const fr_t* const* d_scalars, uint32_t bas
 #undef ZK_LAT_BUCKETS
         static DeviceOnce once;
         once.run([] { ZK_CUDA(cudaFuncSetAttribute(k_lat_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * (int)sizeof(g1_xyzz_t))); });
-        ZK_LAUNCH(k_lat_heavy, 128, 512, 512 * sizeof(g1_xyzz_t), st, d_tables, ws.offsets.p, ws.entries.p, D, ws.buckets.p, ws.heavy_count.p, ws.heavy_list.p);
+        // partial sums + completion counters for as many heavy buckets as the worklist can hold
+        const size_t max_heavy = M * plan.entries_per_msm() / ZK_HEAVY_MIN + 1;
+        ws.heavy_partial.ensure(max_heavy * ZK_LAT_HEAVY_SPLIT);
+        ws.heavy_done.ensure(max_heavy);
+        ZK_CUDA(cudaMemsetAsync(ws.heavy_done.p, 0, max_heavy * sizeof(uint32_t), st));
+        ZK_LAUNCH(k_lat_heavy, 128 * ZK_LAT_HEAVY_SPLIT / 4, 512, 512 * sizeof(g1_xyzz_t), st, d_tables, ws.offsets.p, ws.entries.p, D, ws.buckets.p,
+                  ws.heavy_count.p, ws.heavy_list.p, ws.heavy_partial.p, ws.heavy_done.p);
     }
     KtScope kt(KT_MSM_REDUCE, st);
     ws.partial.ensure(M * (K / 32) * 2);

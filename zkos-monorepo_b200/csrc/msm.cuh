@@ -31,6 +31,8 @@ struct MsmWorkspace {
     DevBuf<uint32_t> order;     // M * K bucket keys by decreasing run length
     DevBuf<uint32_t> heavy_count;  // worklist of buckets with long runs (k_msm_heavy)
     DevBuf<uint64_t> heavy_list;
+    DevBuf<g1_xyzz_t> heavy_partial;   // latency path: partial sums of the CTAs sharing a heavy bucket
+    DevBuf<uint32_t> heavy_done;       //               and their completion counters
     void ensure(const MsmPlan& p, size_t M);
 };
 
