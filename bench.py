@@ -52,6 +52,7 @@ KT_NAMES = ["msm_bucket_accumulate", "msm_digit_sort", "msm_bucket_reduce", "ntt
             "poly_algebra", "lookup_permute", "misc_blind_chacha_normalize", "host_fiat_shamir_gap"]
 MIX_TYPES = ["new_account", "deposit", "withdraw"]
 MIX_WEIGHTS = [1, 2, 2]
+STRICT = False           # --strict: a timing-class coverage below 0.97 is an error instead of a field of the line
 
 
 def parse():
@@ -69,6 +70,7 @@ def parse():
     ap.add_argument("--cpu-sample-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="default workload only: skip withdraw_lookup / mixed_stream / msm24")
+    ap.add_argument("--strict", action="store_true", help="fail if the kernel-class timers cover less than 97 %% of the timed step")
     return ap.parse_args()
 
 
@@ -444,9 +446,14 @@ def timing_coverage(kt, ms_ktimed, devices=1):
     s = sum(v[0] for v in kt.values()) / devices      # the class timers add up over the devices of a single-process run
     k = s - kt.get("host_fiat_shamir_gap", (0.0, 0))[0] / devices
     cov = s / ms_ktimed if ms_ktimed else None
-    assert cov is None or cov >= 0.97, "kernel-class timers cover only %.1f %% of the timed step: a kernel is missing from the classes" % (100 * cov)
+    ok = cov is None or cov >= 0.97 or devices > 1     # several devices in one process: the wall time also holds their imbalance
+    if STRICT:
+        assert ok, "kernel-class timers cover only %.1f %% of the timed step: a kernel is missing from the classes" % (100 * cov)
+    elif not ok:
+        print("WARNING: kernel-class timers cover only %.1f %% of the timed step" % (100 * cov), file=sys.stderr)
     return {"sum_of_kernel_classes_ms": round(k, 3), "host_gap_ms": round(s - k, 3), "timed_step_ms": round(ms_ktimed, 3),
-            "covered": round(cov, 4) if cov is not None else None, "untimed_share": round(1 - cov, 4) if cov is not None else None}
+            "covered": round(cov, 4) if cov is not None else None, "untimed_share": round(1 - cov, 4) if cov is not None else None,
+            "at_least_0.97": bool(ok)}
 
 
 def request_stream(n, seed=7):
@@ -641,7 +648,9 @@ def cpu_check_mixed(env, mx):
 
 
 def main():
+    global STRICT
     args = parse()
+    STRICT = args.strict
     if args.impl == "reference":
         return run_reference(args)
     env = Env(args)

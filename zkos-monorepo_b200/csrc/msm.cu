@@ -959,14 +959,13 @@ void msm_lat_run(const MsmPlan& plan, const fr_t* const* d_scalars, uint32_t bas
     {
         KtScope kt(KT_MSM_BUCKETS, st);
         ZK_CUDA(cudaMemsetAsync(ws.heavy_count.p, 0, sizeof(uint32_t), st));
-        // threads per bucket: as few as still give every SM ~16 warps (the additions of a thread are dependent; the fold across the
-        // TPB threads of a bucket costs log2 TPB more), at most 128 (one CTA per bucket)
+        // threads per bucket: 32 — measured (profiles/r02_single_proof.md) 5.0 G additions/s at 8 MSMs; 8 threads per bucket (fewer,
+        // longer chains, 1.3 waves of CTAs) reached 3.1 G/s on the 24 advice commitments — or a whole CTA per bucket when even that
+        // leaves SMs without work
         const size_t nbk = M * K;
-        const size_t fill = (size_t)148 * 512;
 #define ZK_LAT_BUCKETS(TPB) ZK_LAUNCH(k_lat_buckets<TPB>, ceil_div(nbk * TPB, 128), 128, 0, st, d_tables, ws.offsets.p, ws.entries.p, D, M, ws.buckets.p, \
                                       ws.heavy_count.p, ws.heavy_list.p)
-        if (nbk * 8 >= fill) ZK_LAT_BUCKETS(8);
-        else if (nbk * 32 >= fill) ZK_LAT_BUCKETS(32);
+        if (nbk * 32 >= (size_t)148 * 512) ZK_LAT_BUCKETS(32);
         else ZK_LAT_BUCKETS(128);
 #undef ZK_LAT_BUCKETS
         static DeviceOnce once;

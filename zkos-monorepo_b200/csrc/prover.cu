@@ -205,8 +205,14 @@ struct PkShared;
 // whatever is waiting into one lock-step sub-batch each.  No caller ever queues on a mutex around the GPU.
 struct Coalescer {
     std::mutex mu;
-    std::condition_variable cv_work, cv_done;
+    std::condition_variable cv_work, cv_done, cv_slot;
     std::deque<ProveReq*> q;
+    // Pinned staging slots (one request's advice columns each).  A caller copies its advice into a slot BEFORE it queues — the
+    // hundred callers do that in parallel, on their own threads — so a dispatcher's upload of a sub-batch is one burst of DMA from
+    // pinned memory instead of B staged copies from pageable buffers on the dispatcher's thread.
+    std::vector<void*> free_slots;
+    size_t slots_allocated = 0;
+    static const size_t MAX_SLOTS = 256;
     unsigned idle = 0;
     bool stop = false;
     std::vector<std::thread> threads;
@@ -1309,6 +1315,27 @@ PkShared::~PkShared() {
     { std::lock_guard<std::mutex> lk(co.mu); co.stop = true; }
     co.cv_work.notify_all();
     for (auto& t : co.threads) if (t.joinable()) t.join();
+    for (void* p : co.free_slots) cudaFreeHost(p);
+}
+// a pinned staging slot for one request (blocks while all MAX_SLOTS are in use)
+static void* acquire_slot(Coalescer& co, size_t bytes) {
+    std::unique_lock<std::mutex> lk(co.mu);
+    for (;;) {
+        if (!co.free_slots.empty()) { void* p = co.free_slots.back(); co.free_slots.pop_back(); return p; }
+        if (co.slots_allocated < Coalescer::MAX_SLOTS) {
+            ++co.slots_allocated;
+            lk.unlock();
+            void* p = nullptr;
+            cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+            if (e != cudaSuccess) { cudaGetLastError(); lk.lock(); --co.slots_allocated; throw Error(ZK_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+            return p;
+        }
+        co.cv_slot.wait(lk);
+    }
+}
+static void release_slot(Coalescer& co, void* p) {
+    { std::lock_guard<std::mutex> lk(co.mu); co.free_slots.push_back(p); }
+    co.cv_slot.notify_one();
 }
 
 }  // namespace zk
@@ -1437,17 +1464,23 @@ int zkgpu_prove(uint64_t pk, const uint64_t* advice, const uint64_t* instance, s
     std::shared_ptr<PkShared> P = find_pk(pk);
     check_batch_args(*P->dev[0], advice, instance, num_instance, 1, rng_data, proof_out, proof_len, rng_mode);
     std::call_once(P->co_once, start_dispatchers, P.get());
-    ProveReq req;
-    req.advice = reinterpret_cast<const fr_t*>(advice); req.instance = reinterpret_cast<const fr_t*>(instance); req.num_pi = num_instance;
-    req.rng_mode = rng_mode; req.rng_data = static_cast<uint8_t*>(rng_data); req.proof_out = proof_out;
     Coalescer& co = P->co;
+    const PkEntry& pk0 = *P->dev[0];
+    const size_t adv_bytes = (size_t)pk0.A * pk0.n * sizeof(fr_t);
+    pk0.C->bind();
+    void* slot = acquire_slot(co, adv_bytes);
+    memcpy(slot, advice, adv_bytes);
+    ProveReq req;
+    req.advice = static_cast<const fr_t*>(slot); req.instance = reinterpret_cast<const fr_t*>(instance); req.num_pi = num_instance;
+    req.rng_mode = rng_mode; req.rng_data = static_cast<uint8_t*>(rng_data); req.proof_out = proof_out;
     {
         std::unique_lock<std::mutex> lk(co.mu);
-        ZK_REQUIRE(!co.stop, "proving key is being released");
+        if (co.stop) { lk.unlock(); release_slot(co, slot); throw Error(ZK_ERR_STATE, "proving key is being released"); }
         co.q.push_back(&req);
         co.cv_work.notify_all();
         co.cv_done.wait(lk, [&] { return req.done; });
     }
+    release_slot(co, slot);
     if (req.rc != ZKGPU_OK) throw Error(req.rc, req.err);
     if (req.status == PROOF_LOOKUP_FAILED)
         throw Error(ZKGPU_ERR_WITNESS, "create_proof: a lookup input is not in its table (ConstraintSystemFailure)");
