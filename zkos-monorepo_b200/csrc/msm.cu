@@ -959,13 +959,20 @@ void msm_lat_run(const MsmPlan& plan, const fr_t* const* d_scalars, uint32_t bas
     {
         KtScope kt(KT_MSM_BUCKETS, st);
         ZK_CUDA(cudaMemsetAsync(ws.heavy_count.p, 0, sizeof(uint32_t), st));
-        // threads per bucket: 32 — measured (profiles/r02_single_proof.md) 5.0 G additions/s at 8 MSMs; 8 threads per bucket (fewer,
-        // longer chains, 1.3 waves of CTAs) reached 3.1 G/s on the 24 advice commitments — or a whole CTA per bucket when even that
-        // leaves SMs without work
+        // Threads per bucket (TPB).  A CTA of 128 threads serves 128 / TPB buckets; a thread issues mean / TPB mixed additions plus
+        // log2(TPB) fold additions (paid by the whole warp however few lanes are still active), and 592 CTAs are resident at a time.
+        // Measured on the withdraw proof (profiles/r02_single_proof.md; c = 10, 416 points per bucket on average):
+        //   24 MSMs: TPB 16 1311 us, 32 1487 us, 8 1490-1634 us   |   8 MSMs: TPB 32 372 us, 16 482 us
+        //    5 MSMs: TPB 32 405 us, 16 514 us                     |   1 MSM : TPB 128 128 us
         const size_t nbk = M * K;
+        unsigned tpb = nbk >= 8192 ? 16 : nbk >= 1536 ? 32 : 128;
+        static const unsigned tpb_force = [] { const char* e = getenv("ZKGPU_LAT_TPB"); int v = e ? atoi(e) : 0; return (unsigned)((v == 16 || v == 32 || v == 64 || v == 128) ? v : 0); }();
+        if (tpb_force) tpb = tpb_force;
 #define ZK_LAT_BUCKETS(TPB) ZK_LAUNCH(k_lat_buckets<TPB>, ceil_div(nbk * TPB, 128), 128, 0, st, d_tables, ws.offsets.p, ws.entries.p, D, M, ws.buckets.p, \
                                       ws.heavy_count.p, ws.heavy_list.p)
-        if (nbk * 32 >= (size_t)148 * 512) ZK_LAT_BUCKETS(32);
+        if (tpb == 16) ZK_LAT_BUCKETS(16);
+        else if (tpb == 32) ZK_LAT_BUCKETS(32);
+        else if (tpb == 64) ZK_LAT_BUCKETS(64);
         else ZK_LAT_BUCKETS(128);
 #undef ZK_LAT_BUCKETS
         static DeviceOnce once;
