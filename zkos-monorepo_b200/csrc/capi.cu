@@ -154,7 +154,8 @@ void Context::msm_srs_dev(SrsEntry& S, int basis, const fr_t* d_scalars, size_t 
         lp.n = n; lp.tstride = S.n;
         const fr_t* sc[ZK_LAT_MAX_M];
         for (size_t i = 0; i < m; ++i) sc[i] = d_scalars + i * n;
-        msm_lat_run(lp, sc, basis ? ~0u : 0u, S.lat_stride(), S.lat_tables.p, m, d_out_affine, ws, st);
+        if (S.direct_tables.p) msm_direct_run(sc, basis ? ~0u : 0u, S.direct_stride, S.direct_tables.p, n, S.n, m, d_out_affine, ws, st);
+        else msm_lat_run(lp, sc, basis ? ~0u : 0u, S.lat_stride(), S.lat_tables.p, m, d_out_affine, ws, st);
         return;
     }
     MsmPlan plan = S.plan;
@@ -277,6 +278,15 @@ int zkgpu_srs_register(const uint64_t* g, const uint64_t* g_lagrange, uint32_t k
                 msm_precompute_table(S->lat_plan, C.pt_buf.p, S->lat_tables.p + (size_t)b * S->n * S->lat_plan.W, st);
             }
             ZK_CUDA(cudaStreamSynchronize(st));
+            // all multiples for the direct path, if they fit comfortably (a quarter of the free HBM at most)
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            const size_t stride = msm_direct_points_per_basis(S->n);
+            if (msm_direct_enabled() && k <= 15 && 2 * stride * sizeof(g1_affine_t) <= free_b / 4) {
+                S->direct_tables.alloc(2 * stride);
+                S->direct_stride = stride;
+                for (int b = 0; b < 2; ++b) msm_direct_build(S->lat_tables.p + (size_t)b * S->lat_stride(), S->n, S->direct_tables.p + (size_t)b * stride, st);
+            }
         }
         std::unique_lock<std::shared_mutex> tl(R.tab_mu);
         C.srs[h] = std::move(S);

@@ -27,6 +27,10 @@ struct SrsEntry {
     MsmPlan lat_plan;
     DevBuf<g1_affine_t> lat_tables;   // [2][W_lat][n]: g, then g_lagrange
     size_t lat_stride() const { return n * lat_plan.W; }
+    // direct plan: every multiple d * 2^(8 w) * G_i (d <= 128) of both bases, so that a few MSMs are plain sums of table entries
+    // (msm.cu "Direct path"; 2.1 GB per basis at n = 2^13)
+    DevBuf<g1_affine_t> direct_tables;   // [2][W][n][128]
+    size_t direct_stride = 0;            // points per basis
 };
 
 struct Context {

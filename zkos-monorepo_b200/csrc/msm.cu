@@ -771,6 +771,140 @@ __global__ void __launch_bounds__(32) k_lat_reduce_b(const g1_xyzz_t* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Direct path: the commitments of one proof WITHOUT buckets.
+// With a few MSMs in flight the bucket method pays for its structure, not for its additions: a digit sort, bucket folds and a
+// bucket reduction of ~25 dependent point additions per round (~0.35 ms for one MSM).  The SRS bases are fixed, so the table can
+// hold every multiple a digit can ask for: D[w][i][d-1] = d * 2^(c w) * G_i for d = 1 .. 2^(c-1) (c = 8: 32 windows x n x 128
+// points = 2.1 GB per basis at n = 2^13; HBM has 180 GB).  An MSM is then the plain sum of n * W table entries
+//     sum_i s_i G_i = sum_{i,w} sign(d_iw) * D[w][i][|d_iw| - 1]
+// — no sort, no buckets, no reduction, nothing that a constant column can skew: every thread adds its share of entries into one
+// accumulator (k_direct_sum: units of 128 points x 8 windows, then a shared-memory tree per CTA) and a second small kernel
+// folds the CTAs' partial sums and normalises (k_direct_fold).
+// Signed digits come from the recoding  d_w = ((s + H) >> c w) & (2^c - 1)) - 2^(c-1),  H = 2^(c-1) * sum_w 2^(c w):  every window's
+// digit is independent of the others (no carry chain), in [-2^(c-1), 2^(c-1) - 1]; c * W = 256 so the sum is exact mod 2^256 and
+// s + H < 2^256 for s < r.
+// ---------------------------------------------------------------------------------------------
+#define ZK_DIRECT_C 8
+#define ZK_DIRECT_W 32
+#define ZK_DIRECT_D 128          // 2^(c-1) multiples per (window, point)
+#define ZK_DIRECT_WG 8           // windows per thread
+// tmp[i * D + d - 1] = d * base[i] (XYZZ), one thread per point
+__global__ void __launch_bounds__(64) k_direct_multiples(const g1_affine_t* __restrict__ base, g1_xyzz_t* __restrict__ tmp, unsigned n) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_affine_t p;
+    p.x = fe_load(&base[i].x); p.y = fe_load(&base[i].y);
+    g1_xyzz_t acc = g1_xyzz_t::identity();
+    for (unsigned d = 0; d < ZK_DIRECT_D; ++d) {
+        xyzz_madd(acc, p, false);
+        xyzz_store(tmp + (size_t)i * ZK_DIRECT_D + d, acc);
+    }
+}
+// affine normalisation of the D multiples of one point with ONE inversion (Montgomery's trick over u_d = ZZ_d * ZZZ_d);
+// pre[i * D + d] is scratch for the prefix products
+__global__ void __launch_bounds__(64) k_direct_normalize(const g1_xyzz_t* __restrict__ tmp, fq_t* __restrict__ pre, g1_affine_t* __restrict__ out, unsigned n) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const g1_xyzz_t* t = tmp + (size_t)i * ZK_DIRECT_D;
+    fq_t* pr = pre + (size_t)i * ZK_DIRECT_D;
+    g1_affine_t* o = out + (size_t)i * ZK_DIRECT_D;
+    const fq_t one = fe_one<FqTag>();
+    fq_t acc = one;
+    for (unsigned d = 0; d < ZK_DIRECT_D; ++d) {
+        fe_store(pr + d, acc);
+        fq_t zz = fe_load(&t[d].zz);
+        if (!zz.is_zero()) acc = acc * (zz * fe_load(&t[d].zzz));
+    }
+    fq_t inv = fe_inv(acc);
+    for (unsigned d = ZK_DIRECT_D; d-- > 0;) {
+        fq_t zz = fe_load(&t[d].zz), zzz = fe_load(&t[d].zzz);
+        if (zz.is_zero()) { fe_store(&o[d].x, fq_t::zero()); fe_store(&o[d].y, fq_t::zero()); continue; }   // multiple of the identity
+        fq_t tinv = inv * fe_load(pr + d);       // 1 / (ZZ ZZZ)
+        inv = inv * (zz * zzz);
+        fe_store(&o[d].x, fe_load(&t[d].x) * (zzz * tinv));
+        fe_store(&o[d].y, fe_load(&t[d].y) * (zz * tinv));
+    }
+}
+
+struct DirectArgs {
+    const fr_t* sc[ZK_LAT_MAX_M];
+    uint32_t basis_mask;
+    size_t table_stride;   // points between the two bases' tables
+    unsigned n, tstride;   // scalars per MSM; points per window in the table (the SRS size)
+};
+// A unit of work = 128 points x WG windows (one madd per thread and window).  grid: (ctas_per_msm, M); CTA c of an MSM takes the
+// units [c U / C, (c + 1) U / C), U = (n / 128) * (W / WG): the host picks C so that ALL CTAs of the launch are resident at once
+// (no partial last wave) and a thread's chain is as long as that allows, which amortises the CTA's fold tree.
+__global__ void __launch_bounds__(128, 4) k_direct_sum(DirectArgs A, const g1_affine_t* __restrict__ table, unsigned units, g1_xyzz_t* __restrict__ partial) {
+    __shared__ g1_xyzz_t part[128];
+    const unsigned m = blockIdx.y, C = gridDim.x;
+    const g1_affine_t* T = table + ((A.basis_mask >> m) & 1u) * A.table_stride;
+    g1_xyzz_t acc = g1_xyzz_t::identity();
+    const unsigned u0 = (unsigned)(((uint64_t)blockIdx.x * units) / C), u1 = (unsigned)(((uint64_t)(blockIdx.x + 1) * units) / C);
+    const unsigned groups = ZK_DIRECT_W / ZK_DIRECT_WG;
+    unsigned cur_chunk = ~0u;
+    uint32_t sl[8];
+#pragma unroll 1
+    for (unsigned u = u0; u < u1; ++u) {
+        const unsigned chunk = u / groups, wg = u % groups;     // consecutive units of a chunk share the scalar
+        const unsigned i = chunk * 128 + threadIdx.x;
+        if (i >= A.n) continue;
+        if (chunk != cur_chunk) {
+            fr_t s = from_mont(fe_load(A.sc[m] + i));
+            // s + H, H = 0x80 in every byte (c = 8)
+            uint32_t carry = 0;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) { uint64_t v = (uint64_t)s.l[l] + 0x80808080u + carry; sl[l] = (uint32_t)v; carry = (uint32_t)(v >> 32); }
+            cur_chunk = chunk;
+        }
+        const uint32_t dlo = wg == 0 ? sl[0] : wg == 1 ? sl[2] : wg == 2 ? sl[4] : sl[6];   // (selects, not a dynamically indexed array)
+        const uint32_t dhi = wg == 0 ? sl[1] : wg == 1 ? sl[3] : wg == 2 ? sl[5] : sl[7];
+        const uint64_t dig = ((uint64_t)dhi << 32) | dlo;   // the 8 digit bytes of this window group
+        // the table entry of window j + 1 is in flight (a random 64-byte read from a multi-gigabyte table: DRAM latency) while
+        // window j's point is added; a zero digit loads entry 0 and skips the addition
+        auto entry = [&](unsigned j) -> const g1_affine_t* {
+            const int d = (int)((dig >> (8 * j)) & 0xffu) - 128;
+            const unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
+            return T + ((size_t)(wg * ZK_DIRECT_WG + j) * A.tstride + i) * ZK_DIRECT_D + (mag ? mag - 1 : 0);
+        };
+        const g1_affine_t* p = entry(0);
+        g1_affine_t q;
+        q.x = fe_ldg(&p->x); q.y = fe_ldg(&p->y);
+#pragma unroll 1
+        for (unsigned j = 0; j < ZK_DIRECT_WG; ++j) {
+            g1_affine_t qn = q;
+            if (j + 1 < ZK_DIRECT_WG) { const g1_affine_t* pn = entry(j + 1); qn.x = fe_ldg(&pn->x); qn.y = fe_ldg(&pn->y); }
+            const int d = (int)((dig >> (8 * j)) & 0xffu) - 128;
+            if (d != 0) xyzz_madd(acc, q, d < 0);
+            q = qn;
+        }
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (unsigned s2 = 64; s2 > 0; s2 >>= 1) {
+        if (threadIdx.x < s2) part[threadIdx.x] = xyzz_add(part[threadIdx.x], part[threadIdx.x + s2]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) xyzz_store(partial + (size_t)m * C + blockIdx.x, part[0]);
+}
+// one CTA per MSM folds its `count` partial sums (count <= 256, a power of two) and writes the affine result
+__global__ void __launch_bounds__(256) k_direct_fold(const g1_xyzz_t* __restrict__ partial, unsigned count, g1_affine_t* __restrict__ out) {
+    extern __shared__ uint4 direct_fold_sm[];
+    g1_xyzz_t* part = reinterpret_cast<g1_xyzz_t*>(direct_fold_sm);
+    const unsigned t = threadIdx.x;
+    part[t] = t < count ? xyzz_load(partial + (size_t)blockIdx.x * count + t) : g1_xyzz_t::identity();
+    __syncthreads();
+    for (unsigned s2 = blockDim.x >> 1; s2 > 0; s2 >>= 1) {
+        if (t < s2) part[t] = xyzz_add(part[t], part[t + s2]);
+        __syncthreads();
+    }
+    if (t == 0) {
+        g1_affine_t a = xyzz_to_affine(part[0]);
+        fe_store(&out[blockIdx.x].x, a.x); fe_store(&out[blockIdx.x].y, a.y);
+    }
+}
+
 __global__ void k_msm_combine(const g1_xyzz_t* __restrict__ groups, MsmDims D, size_t M, g1_xyzz_t* __restrict__ out) {
     size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
@@ -929,7 +1063,7 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
 }
 
 unsigned msm_lat_window() {
-    static const unsigned c = [] { const char* e = getenv("ZKGPU_LAT_C"); int v = e ? atoi(e) : 10; return (unsigned)((v >= 6 && v <= 10) ? v : v == 0 ? 0 : 10); }();
+    static const unsigned c = [] { const char* e = getenv("ZKGPU_LAT_C"); int v = e ? atoi(e) : 8; return (unsigned)((v >= 6 && v <= 10) ? v : v == 0 ? 0 : 8); }();
     return c;
 }
 
@@ -989,6 +1123,46 @@ void msm_lat_run(const MsmPlan& plan, const fr_t* const* d_scalars, uint32_t bas
     ws.partial.ensure(M * (K / 32) * 2);
     ZK_LAUNCH(k_lat_reduce_a, dim3((unsigned)(K / 32), (unsigned)M), 32, 0, st, ws.buckets.p, D, ws.partial.p);
     ZK_LAUNCH(k_lat_reduce_b, (unsigned)M, 32, 0, st, ws.partial.p, D, d_out_affine);
+}
+
+// ---- direct path, host side ----
+size_t msm_direct_points_per_basis(size_t n) { return (size_t)ZK_DIRECT_W * n * ZK_DIRECT_D; }
+bool msm_direct_enabled() {
+    static const bool on = [] { const char* e = getenv("ZKGPU_DIRECT"); return e ? atoi(e) != 0 : true; }();
+    return on && msm_lat_window() == ZK_DIRECT_C;
+}
+// window_table: T[w][i] = 2^(8 w) * base[i] (the latency plan's table for c = 8, W = 32); direct[(w * n + i) * D + d - 1] = d * T[w][i]
+void msm_direct_build(const g1_affine_t* d_window_table, size_t n, g1_affine_t* d_direct, cudaStream_t st) {
+    DevBuf<g1_xyzz_t> tmp(n * ZK_DIRECT_D);
+    DevBuf<fq_t> pre(n * ZK_DIRECT_D);
+    for (unsigned w = 0; w < ZK_DIRECT_W; ++w) {
+        ZK_LAUNCH(k_direct_multiples, ceil_div(n, 64), 64, 0, st, d_window_table + (size_t)w * n, tmp.p, (unsigned)n);
+        ZK_LAUNCH(k_direct_normalize, ceil_div(n, 64), 64, 0, st, tmp.p, pre.p, d_direct + (size_t)w * n * ZK_DIRECT_D, (unsigned)n);
+    }
+    ZK_CUDA(cudaStreamSynchronize(st));
+}
+void msm_direct_run(const fr_t* const* d_scalars, uint32_t basis_mask, size_t table_stride, const g1_affine_t* d_direct, size_t n, size_t tstride,
+                    size_t M, g1_affine_t* d_out_affine, MsmWorkspace& ws, cudaStream_t st) {
+    if (M == 0) return;
+    ZK_REQUIRE(M <= ZK_LAT_MAX_M && n >= 1 && n <= tstride, "msm_direct_run: unsupported shape");
+    DirectArgs A;
+    for (size_t m = 0; m < ZK_LAT_MAX_M; ++m) A.sc[m] = d_scalars[m < M ? m : 0];
+    A.basis_mask = basis_mask; A.table_stride = table_stride; A.n = (unsigned)n; A.tstride = (unsigned)tstride;
+    // CTAs per MSM: all CTAs of the launch resident at once (148 SMs x 4 CTAs of 128 threads at 128 registers), at most one unit each
+    const unsigned units = ceil_div(n, 128) * (ZK_DIRECT_W / ZK_DIRECT_WG);
+    unsigned ctas = (unsigned)(((size_t)148 * 4) / M);
+    if (ctas > units) ctas = units;
+    if (ctas > 256) ctas = 256;
+    if (ctas < 1) ctas = 1;
+    unsigned folded = 1;
+    while (folded < ctas) folded <<= 1;       // partial sums per MSM, padded to a power of two for the fold tree
+    ws.partial.ensure(M * ctas);
+    {
+        KtScope kt(KT_MSM_BUCKETS, st);
+        ZK_LAUNCH(k_direct_sum, dim3(ctas, (unsigned)M), 128, 0, st, A, d_direct, units, ws.partial.p);
+    }
+    KtScope kt(KT_MSM_REDUCE, st);
+    ZK_LAUNCH(k_direct_fold, (unsigned)M, folded, folded * sizeof(g1_xyzz_t), st, ws.partial.p, ctas, d_out_affine);
 }
 
 void msm_precompute_table(const MsmPlan& plan, const g1_affine_t* d_bases, g1_affine_t* d_table, cudaStream_t st) {

@@ -138,7 +138,16 @@ struct ProverWs {
     cudaEvent_t ev_pts = nullptr;    // "commitments of step 2 copied back" marker, reused by every sub-batch
     DevBuf<fr_t> adv_next;
     const fr_t* prefetched_src = nullptr;
+    // single-proof regime: the advice / instance transforms run on a side stream WHILE the advice commitments are computed
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_blind = nullptr, ev_side = nullptr, ev_z = nullptr, ev_zside = nullptr;
+    DevBuf<fr_t> adv_coef, inst_coef, z_coef, nd, scratch2;
     ~ProverWs() {
+        if (side) cudaStreamDestroy(side);
+        if (ev_blind) cudaEventDestroy(ev_blind);
+        if (ev_side) cudaEventDestroy(ev_side);
+        if (ev_z) cudaEventDestroy(ev_z);
+        if (ev_zside) cudaEventDestroy(ev_zside);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (copy_ev) cudaEventDestroy(copy_ev);
@@ -260,28 +269,32 @@ static void host_batch_invert(std::vector<fr_t>& v) {
 static const size_t SCRATCH_ELEMS = (size_t)1 << 25;  // 1 GiB of two-pass NTT scratch
 
 // lagrange_to_coeff on `count` contiguous polynomials of 2^k values, in place
-static void intt_n(PkEntry& pk, ProverWs& W, fr_t* p, size_t count, cudaStream_t st) {
+// (out: where the coefficients go, default in place; scratch: which staging buffer, default the worker's)
+static void intt_n(PkEntry& pk, ProverWs& W, fr_t* p, size_t count, cudaStream_t st, fr_t* out = nullptr, DevBuf<fr_t>* scratch = nullptr) {
     const bool two = ntt_scratch_elems(pk.k, 1) != 0;   // two-pass transforms stage through a scratch buffer, chunk by chunk
+    DevBuf<fr_t>& S = scratch ? *scratch : W.scratch;
     size_t per = two ? std::max<size_t>(1, SCRATCH_ELEMS >> pk.k) : count;
-    if (two) W.scratch.ensure(std::min(count, per) << pk.k);
+    if (two) S.ensure(std::min(count, per) << pk.k);
     for (size_t off = 0; off < count; off += per) {
         NttJob J;
-        J.in = J.out = p + (off << pk.k); J.scratch = W.scratch.p; J.batch = std::min(per, count - off); J.log_n = pk.k;
+        J.in = p + (off << pk.k); J.out = (out ? out : p) + (off << pk.k); J.scratch = S.p; J.batch = std::min(per, count - off); J.log_n = pk.k;
         J.omega = pk.omega_inv; J.has_scale = 1; J.scale = pk.n_inv;
         ntt_run(J, st);
     }
 }
 // coefficients -> values on the Qc quotient cosets: groups x cols polynomials at in[(g*cols + c)*n] -> out[g*out_group_stride + c*cn],
 // each output column coset-major [Qc][n].  Every coset is one size-n NTT of a[m] * g_c^m (table pk.coset_pows).
-static void coset_ext(PkEntry& pk, ProverWs& W, const fr_t* in, fr_t* out, size_t groups, size_t cols, size_t out_group_stride, cudaStream_t st) {
+static void coset_ext(PkEntry& pk, ProverWs& W, const fr_t* in, fr_t* out, size_t groups, size_t cols, size_t out_group_stride, cudaStream_t st,
+                      DevBuf<fr_t>* scratch = nullptr) {
     const bool two = ntt_scratch_elems(pk.k, 1) != 0;
+    DevBuf<fr_t>& S = scratch ? *scratch : W.scratch;
     const size_t per_group = cols * pk.Qc;
     size_t per = two ? std::max<size_t>(1, (SCRATCH_ELEMS >> pk.k) / per_group) : groups;
-    if (two) W.scratch.ensure((std::min(groups, per) * per_group) << pk.k);
+    if (two) S.ensure((std::min(groups, per) * per_group) << pk.k);
     for (size_t off = 0; off < groups; off += per) {
         size_t g = std::min(per, groups - off);
         NttJob J;
-        J.in = in + off * cols * pk.n; J.out = out + off * out_group_stride; J.scratch = W.scratch.p;
+        J.in = in + off * cols * pk.n; J.out = out + off * out_group_stride; J.scratch = S.p;
         J.batch = g * per_group; J.log_n = pk.k; J.omega = pk.omega;
         J.in_broadcast = 1; J.in_inner = pk.Qc; J.in_outer_stride = pk.n;
         J.out_stride = pk.n; J.out_inner = per_group; J.out_outer_stride = out_group_stride;
@@ -303,7 +316,8 @@ static void commit_lat(Context& C, PkEntry& pk, ProverWs& W, const std::vector<C
     const fr_t* sc[ZK_LAT_MAX_M];
     uint32_t mask = 0;
     for (size_t m = 0; m < items.size(); ++m) { sc[m] = items[m].scalars; if (items[m].basis) mask |= 1u << m; }
-    msm_lat_run(plan, sc, mask, S.lat_stride(), S.lat_tables.p, items.size(), d_out, W.msm, st);
+    if (S.direct_tables.p) msm_direct_run(sc, mask, S.direct_stride, S.direct_tables.p, pk.n, S.n, items.size(), d_out, W.msm, st);
+    else msm_lat_run(plan, sc, mask, S.lat_stride(), S.lat_tables.p, items.size(), d_out, W.msm, st);
 }
 
 // M commitments; MSM m reads scalars at (m / inner) * outer_stride + (m % inner) * n.  Affine out.
@@ -769,6 +783,28 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
     // ---- step 1: blind + commit advice --------------------------------------------------------
     launch_scatter_random(W.adv.p, A * n, n, pk.ustart, W.raw_adv.p, B, A, bf + 1, st);
     trace_dev("advice_blinded", W.adv.p, n, A, n, st);
+    // Single-proof regime: the advice commitments leave most of the GPU idle (a few dozen MSMs), and the advice / instance
+    // transforms need nothing but the blinded values: they run on a side stream meanwhile, into separate buffers (the Lagrange
+    // values are still needed by the lookup and permutation arguments), and the buffers are swapped where the in-place transform
+    // would have happened.
+    const bool overlap = commit_lat_ok(C, pk, B * A) && !g_trace;
+    if (overlap) {
+        if (!W.side) {
+            ZK_CUDA(cudaStreamCreateWithFlags(&W.side, cudaStreamNonBlocking));
+            ZK_CUDA(cudaEventCreateWithFlags(&W.ev_blind, cudaEventDisableTiming));
+            ZK_CUDA(cudaEventCreateWithFlags(&W.ev_side, cudaEventDisableTiming));
+            ZK_CUDA(cudaEventCreateWithFlags(&W.ev_z, cudaEventDisableTiming));
+            ZK_CUDA(cudaEventCreateWithFlags(&W.ev_zside, cudaEventDisableTiming));
+        }
+        W.adv_coef.ensure(W.adv.n); W.inst_coef.ensure(W.inst.n); W.nd.ensure(std::max<size_t>(1, 2 * B * (P + L) * n));
+        ZK_CUDA(cudaEventRecord(W.ev_blind, st));
+        ZK_CUDA(cudaStreamWaitEvent(W.side, W.ev_blind, 0));
+        intt_n(pk, W, W.adv.p, B * A, W.side, W.adv_coef.p, &W.scratch2);
+        intt_n(pk, W, W.inst.p, B, W.side, W.inst_coef.p, &W.scratch2);
+        coset_ext(pk, W, W.adv_coef.p, W.adv_ext.p, B, A, (A + 1) * en, W.side, &W.scratch2);
+        coset_ext(pk, W, W.inst_coef.p, W.adv_ext.p + A * en, B, 1, (A + 1) * en, W.side, &W.scratch2);
+        ZK_CUDA(cudaEventRecord(W.ev_side, W.side));
+    }
     commit(C, pk, W, 1, W.adv.p, B * A, 0, 0, W.aff.p, st);
     {
         const g1_affine_t* pts = fetch_points(B * A);
@@ -809,7 +845,7 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
     timer.lap(1);
     // ---- step 2: permutation grand products, random polynomial --------------------------------
     if (P) {
-        fr_t* num = W.adv_ext.p; fr_t* den = W.adv_ext.p + B * P * n;  // adv_ext is free until step 4
+        fr_t* num = overlap ? W.nd.p : W.adv_ext.p; fr_t* den = num + B * P * n;  // adv_ext is free until step 4 (unless the side stream fills it)
         PermArgs pa;
         pa.adv = W.adv.p; pa.adv_proof_stride = A * n; pa.inst = W.inst.p; pa.inst_proof_stride = n;
         pa.fixed_vals = pk.fixed_vals.p; pa.sigma_vals = pk.sigma_vals.p; pa.cols = pk.cols.p; pa.delta_pows = pk.delta_pows.p;
@@ -822,9 +858,18 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
         launch_perm_finalize(W.z.p, W.carries.p, pk.k, pk.P, pk.bf, W.raw_z.p, B, st);
     }
     if (P) trace_dev("z", W.z.p, n, P, n, st);
+    if (overlap && P) {
+        // same idea for the permutation products: their transforms run beside the round's commitments
+        W.z_coef.ensure(W.z.n);
+        ZK_CUDA(cudaEventRecord(W.ev_z, st));
+        ZK_CUDA(cudaStreamWaitEvent(W.side, W.ev_z, 0));
+        intt_n(pk, W, W.z.p, B * P, W.side, W.z_coef.p, &W.scratch2);
+        coset_ext(pk, W, W.z_coef.p, W.z_ext.p, B, P, P * en, W.side, &W.scratch2);
+        ZK_CUDA(cudaEventRecord(W.ev_zside, W.side));
+    }
     if (L) {
         // lookup arguments, part 2: grand products
-        fr_t* num = W.adv_ext.p + 2 * B * P * n; fr_t* den = num + B * L * n;
+        fr_t* num = (overlap ? W.nd.p : W.adv_ext.p) + 2 * B * P * n; fr_t* den = num + B * L * n;
         {
             KtScope kt(KT_PERM, st);
             launch_lookup_num_den(W.lk_in.p, W.lk_tab.p, W.lk_a.p, W.lk_s.p, W.ch.p, num, den, pk.k, pk.L, B, st);
@@ -853,7 +898,10 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
     cudaEvent_t ev_pts = W.ev_pts;
     ZK_CUDA(cudaEventRecord(ev_pts, st));
     // queue the transforms that do not depend on y behind the commitments
-    if (P) {
+    if (overlap && P) {
+        ZK_CUDA(cudaStreamWaitEvent(st, W.ev_zside, 0));
+        std::swap(W.z.p, W.z_coef.p); std::swap(W.z.n, W.z_coef.n);
+    } else if (P) {
         intt_n(pk, W, W.z.p, B * P, st);
         coset_ext(pk, W, W.z.p, W.z_ext.p, B, P, P * en, st);
     }
@@ -863,10 +911,16 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
         coset_ext(pk, W, W.lk_a.p, W.lk_ext.p + en, B * L, 1, 3 * en, st);
         coset_ext(pk, W, W.lk_s.p, W.lk_ext.p + 2 * en, B * L, 1, 3 * en, st);
     }
-    intt_n(pk, W, W.adv.p, B * A, st);
-    intt_n(pk, W, W.inst.p, B, st);
-    coset_ext(pk, W, W.adv.p, W.adv_ext.p, B, A, (A + 1) * en, st);
-    coset_ext(pk, W, W.inst.p, W.adv_ext.p + A * en, B, 1, (A + 1) * en, st);
+    if (overlap) {
+        ZK_CUDA(cudaStreamWaitEvent(st, W.ev_side, 0));
+        std::swap(W.adv.p, W.adv_coef.p); std::swap(W.adv.n, W.adv_coef.n);
+        std::swap(W.inst.p, W.inst_coef.p); std::swap(W.inst.n, W.inst_coef.n);
+    } else {
+        intt_n(pk, W, W.adv.p, B * A, st);
+        intt_n(pk, W, W.inst.p, B, st);
+        coset_ext(pk, W, W.adv.p, W.adv_ext.p, B, A, (A + 1) * en, st);
+        coset_ext(pk, W, W.inst.p, W.adv_ext.p + A * en, B, 1, (A + 1) * en, st);
+    }
     ZK_CUDA(cudaEventSynchronize(ev_pts));
     {
         const g1_affine_t* pts = W.h_aff.as<g1_affine_t>();
