@@ -35,4 +35,4 @@ for it in range(int(sys.argv[3]) if len(sys.argv) > 3 else 3):
     proofs = pk.prove_batch(adv, pi, seeds)
     dt = time.time() - t
     zkgpu.lib().zkgpu_prover_step_seconds(steps, 1)
-    print("iter %d: %d proofs in %.3fs = %.1f proofs/s; steps(s): %s" % (it, m, dt, m / dt, " ".join("%.3f" % x for x in steps[:7])))
+    print("iter %d: %d proofs in %.3fs = %.1f proofs/s; steps(s): %s" % (it, m, dt, m / dt, " ".join("%.0f" % (1e6 * x) for x in steps[:8]) + " us"))

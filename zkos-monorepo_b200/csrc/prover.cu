@@ -362,9 +362,30 @@ static void upload_advice(void* dst, const void* src, size_t bytes, cudaStream_t
     }
     ZK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
 }
+// Small host -> device uploads (rng draws, challenges, job lists: a few per Fiat-Shamir step).  From pageable memory every one of
+// them synchronises the stream and is staged by the driver before the call returns (measured: ~50 us each, 0.3 ms of a single proof's
+// first step).  A sub-batch therefore stages them through one pinned arena of its worker: a host memcpy, then a truly asynchronous
+// copy.  The arena is rewound at the start of a sub-batch (the previous one ended with a stream synchronisation); a request that
+// does not fit falls back to the pageable copy.
+struct StageArena {
+    uint8_t* base = nullptr; size_t cap = 0, off = 0;
+    void* put(const void* src, size_t bytes) {
+        const size_t at = (off + 63) & ~(size_t)63;
+        if (!base || at + bytes > cap) return nullptr;
+        memcpy(base + at, src, bytes);
+        off = at + bytes;
+        return base + at;
+    }
+};
+static thread_local StageArena* tl_arena = nullptr;
+static void h2d_bytes(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (!bytes) return;
+    void* staged = tl_arena ? tl_arena->put(src, bytes) : nullptr;
+    ZK_CUDA(cudaMemcpyAsync(dst, staged ? staged : src, bytes, cudaMemcpyHostToDevice, st));
+}
 template <class T>
 static void h2d(T* dst, const std::vector<T>& src, cudaStream_t st) {
-    if (!src.empty()) ZK_CUDA(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    h2d_bytes(dst, src.data(), src.size() * sizeof(T), st);
 }
 template <class T>
 static void upload(DevBuf<T>& buf, const std::vector<T>& src, cudaStream_t st) {
@@ -686,6 +707,11 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
     const size_t ns = pk.plan.sets.size();
     ensure_ws(pk, W, B);
     const fr_t one = fe_one<FrTag>();
+    // pinned staging arena for this sub-batch's small uploads (see StageArena)
+    W.h_stage.ensure(std::max<size_t>((size_t)4 << 20, B * ((size_t)(pk.A + 2 * pk.L + pk.P) * (pk.bf + 1) * 64 + (pk.num_evals + 64) * 128 + 4096)));
+    StageArena arena;
+    arena.base = W.h_stage.as<uint8_t>(); arena.cap = W.h_stage.n;
+    struct ArenaScope { StageArena* prev; explicit ArenaScope(StageArena* a) : prev(tl_arena) { tl_arena = a; } ~ArenaScope() { tl_arena = prev; } } arena_scope(&arena);
 
     StepTimer timer;
     // ---- step 0: transcripts, RNG streams, uploads ------------------------------------------
@@ -730,6 +756,7 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
         for (size_t i = 0; i < Q; ++i) rng.skip_wide();
         rng.store_state(V.rng[b].data);   // a running SmallRng continues after the proof, as `&mut rng` does upstream
     }
+    timer.lap(7);   // host-only part of step 0 (rng streams, transcripts)
     if (V.advice_ptrs) {
         for (size_t b = 0; b < B; ++b)
             ZK_CUDA(cudaMemcpyAsync(W.adv.p + b * A * n, V.advice_ptrs[b], A * n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
@@ -755,8 +782,11 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
         W.prefetched_src = next_advice;
     };
     ZK_CUDA(cudaMemsetAsync(W.inst.p, 0, B * n * sizeof(fr_t), st));
-    if (num_pi)
-        ZK_CUDA(cudaMemcpy2DAsync(W.inst.p, n * sizeof(fr_t), instance, num_pi * sizeof(fr_t), num_pi * sizeof(fr_t), B, cudaMemcpyHostToDevice, st));
+    if (num_pi) {
+        const void* staged = arena.put(instance, B * num_pi * sizeof(fr_t));
+        ZK_CUDA(cudaMemcpy2DAsync(W.inst.p, n * sizeof(fr_t), staged ? staged : (const void*)instance, num_pi * sizeof(fr_t), num_pi * sizeof(fr_t), B,
+                                  cudaMemcpyHostToDevice, st));
+    }
     h2d(W.raw_adv.p, raw_adv, st); h2d(W.raw_z.p, raw_z, st); h2d(W.seeds.p, cseeds, st);
     if (L) { h2d(W.raw_la.p, raw_la, st); h2d(W.raw_ls.p, raw_ls, st); h2d(W.raw_lz.p, raw_lz, st); ZK_CUDA(cudaMemsetAsync(W.d_error.p, 0, B * sizeof(int), st)); }
 
