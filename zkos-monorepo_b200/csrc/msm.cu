@@ -785,12 +785,12 @@ __global__ void __launch_bounds__(32) k_lat_reduce_b(const g1_xyzz_t* __restrict
 // digit is independent of the others (no carry chain), in [-2^(c-1), 2^(c-1) - 1]; c * W = 256 so the sum is exact mod 2^256 and
 // s + H < 2^256 for s < r.
 // ---------------------------------------------------------------------------------------------
-#define ZK_DIRECT_C 8
-#define ZK_DIRECT_W 32
-#define ZK_DIRECT_D 128          // 2^(c-1) multiples per (window, point)
-#define ZK_DIRECT_WG 8           // windows per thread
+#define ZK_DIRECT_WG 8           // windows per unit of work
+// c = 8: W = 32 windows, D = 128 multiples (2.1 GB per basis at n = 2^13); c = 9: W = 29, D = 256 (3.9 GB per basis, 9 % fewer additions)
+__host__ __device__ constexpr unsigned direct_W(unsigned c) { return 254 / c + 1; }
+__host__ __device__ constexpr unsigned direct_D(unsigned c) { return 1u << (c - 1); }
 // tmp[i * D + d - 1] = d * base[i] (XYZZ), one thread per point
-__global__ void __launch_bounds__(64) k_direct_multiples(const g1_affine_t* __restrict__ base, g1_xyzz_t* __restrict__ tmp, unsigned n) {
+__global__ void __launch_bounds__(64) k_direct_multiples(const g1_affine_t* __restrict__ base, g1_xyzz_t* __restrict__ tmp, unsigned n, unsigned ZK_DIRECT_D) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g1_affine_t p;
@@ -803,7 +803,8 @@ __global__ void __launch_bounds__(64) k_direct_multiples(const g1_affine_t* __re
 }
 // affine normalisation of the D multiples of one point with ONE inversion (Montgomery's trick over u_d = ZZ_d * ZZZ_d);
 // pre[i * D + d] is scratch for the prefix products
-__global__ void __launch_bounds__(64) k_direct_normalize(const g1_xyzz_t* __restrict__ tmp, fq_t* __restrict__ pre, g1_affine_t* __restrict__ out, unsigned n) {
+__global__ void __launch_bounds__(64) k_direct_normalize(const g1_xyzz_t* __restrict__ tmp, fq_t* __restrict__ pre, g1_affine_t* __restrict__ out, unsigned n,
+                                                         unsigned ZK_DIRECT_D) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const g1_xyzz_t* t = tmp + (size_t)i * ZK_DIRECT_D;
@@ -836,15 +837,16 @@ struct DirectArgs {
 // A unit of work = 128 points x WG windows (one madd per thread and window).  grid: (ctas_per_msm, M); CTA c of an MSM takes the
 // units [c U / C, (c + 1) U / C), U = (n / 128) * (W / WG): the host picks C so that ALL CTAs of the launch are resident at once
 // (no partial last wave) and a thread's chain is as long as that allows, which amortises the CTA's fold tree.
+template <unsigned CW>
 __global__ void __launch_bounds__(128, 4) k_direct_sum(DirectArgs A, const g1_affine_t* __restrict__ table, unsigned units, g1_xyzz_t* __restrict__ partial) {
     __shared__ g1_xyzz_t part[128];
+    constexpr unsigned W = direct_W(CW), D = direct_D(CW), groups = (W + ZK_DIRECT_WG - 1) / ZK_DIRECT_WG;
     const unsigned m = blockIdx.y, C = gridDim.x;
     const g1_affine_t* T = table + ((A.basis_mask >> m) & 1u) * A.table_stride;
     g1_xyzz_t acc = g1_xyzz_t::identity();
     const unsigned u0 = (unsigned)(((uint64_t)blockIdx.x * units) / C), u1 = (unsigned)(((uint64_t)(blockIdx.x + 1) * units) / C);
-    const unsigned groups = ZK_DIRECT_W / ZK_DIRECT_WG;
     unsigned cur_chunk = ~0u;
-    uint32_t sl[8];
+    uint32_t sl[9];   // s + H: nine limbs (c = 9: 29 windows x 9 bits = 261 bits)
 #pragma unroll 1
     for (unsigned u = u0; u < u1; ++u) {
         const unsigned chunk = u / groups, wg = u % groups;     // consecutive units of a chunk share the scalar
@@ -852,30 +854,53 @@ __global__ void __launch_bounds__(128, 4) k_direct_sum(DirectArgs A, const g1_af
         if (i >= A.n) continue;
         if (chunk != cur_chunk) {
             fr_t s = from_mont(fe_load(A.sc[m] + i));
-            // s + H, H = 0x80 in every byte (c = 8)
+            // s + H, H = 2^(c-1) * sum_w 2^(c w): 0x80 in every byte for c = 8; bits 8, 17, 26, ... for c = 9
             uint32_t carry = 0;
 #pragma unroll
-            for (int l = 0; l < 8; ++l) { uint64_t v = (uint64_t)s.l[l] + 0x80808080u + carry; sl[l] = (uint32_t)v; carry = (uint32_t)(v >> 32); }
+            for (int l = 0; l < 9; ++l) {
+                uint32_t hl = 0;
+                if (CW == 8) hl = l < 8 ? 0x80808080u : 0u;
+                else {
+#pragma unroll
+                    for (unsigned w = 0; w < W; ++w) { const unsigned bit = CW * w + CW - 1; if ((bit >> 5) == (unsigned)l) hl |= 1u << (bit & 31); }
+                }
+                uint64_t v = (uint64_t)(l < 8 ? s.l[l] : 0u) + hl + carry; sl[l] = (uint32_t)v; carry = (uint32_t)(v >> 32);
+            }
             cur_chunk = chunk;
         }
-        const uint32_t dlo = wg == 0 ? sl[0] : wg == 1 ? sl[2] : wg == 2 ? sl[4] : sl[6];   // (selects, not a dynamically indexed array)
-        const uint32_t dhi = wg == 0 ? sl[1] : wg == 1 ? sl[3] : wg == 2 ? sl[5] : sl[7];
-        const uint64_t dig = ((uint64_t)dhi << 32) | dlo;   // the 8 digit bytes of this window group
+        // the (up to) 8 digits of this window group: CW * 8 bits starting at bit CW * 8 * wg — three limbs cover them (selects, not a
+        // dynamically indexed array)
+        const unsigned bit0 = CW * ZK_DIRECT_WG * wg, l0 = bit0 >> 5, sh0 = bit0 & 31;
+        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll
+        for (unsigned l = 0; l < 9; ++l) {
+            if (l == l0) w0 = sl[l];
+            if (l == l0 + 1) w1 = sl[l];
+            if (l == l0 + 2) w2 = sl[l];
+            if (l == l0 + 3) w3 = sl[l];
+        }
+        const uint64_t lo64 = ((uint64_t)w1 << 32) | w0, hi64 = ((uint64_t)w3 << 32) | w2;
+        auto digit = [&](unsigned j) -> int {
+            const unsigned shv = sh0 + CW * j;     // < 32 + 72
+            const uint64_t v = shv == 0 ? lo64 : shv < 64 ? (lo64 >> shv) | (hi64 << (64 - shv)) : hi64 >> (shv - 64);
+            return (int)(v & ((1u << CW) - 1)) - (int)D;
+        };
+        const unsigned nw = W - wg * ZK_DIRECT_WG < ZK_DIRECT_WG ? W - wg * ZK_DIRECT_WG : ZK_DIRECT_WG;   // windows in this group
         // the table entry of window j + 1 is in flight (a random 64-byte read from a multi-gigabyte table: DRAM latency) while
         // window j's point is added; a zero digit loads entry 0 and skips the addition
         auto entry = [&](unsigned j) -> const g1_affine_t* {
-            const int d = (int)((dig >> (8 * j)) & 0xffu) - 128;
+            const int d = digit(j);
             const unsigned mag = d < 0 ? (unsigned)(-d) : (unsigned)d;
-            return T + ((size_t)(wg * ZK_DIRECT_WG + j) * A.tstride + i) * ZK_DIRECT_D + (mag ? mag - 1 : 0);
+            return T + ((size_t)(wg * ZK_DIRECT_WG + j) * A.tstride + i) * D + (mag ? mag - 1 : 0);
         };
         const g1_affine_t* p = entry(0);
         g1_affine_t q;
         q.x = fe_ldg(&p->x); q.y = fe_ldg(&p->y);
 #pragma unroll 1
-        for (unsigned j = 0; j < ZK_DIRECT_WG; ++j) {
+        for (unsigned j = 0; j < nw; ++j) {
             g1_affine_t qn = q;
-            if (j + 1 < ZK_DIRECT_WG) { const g1_affine_t* pn = entry(j + 1); qn.x = fe_ldg(&pn->x); qn.y = fe_ldg(&pn->y); }
-            const int d = (int)((dig >> (8 * j)) & 0xffu) - 128;
+            if (j + 1 < nw) { const g1_affine_t* pn = entry(j + 1); qn.x = fe_ldg(&pn->x); qn.y = fe_ldg(&pn->y); }
+            const int d = digit(j);
             if (d != 0) xyzz_madd(acc, q, d < 0);
             q = qn;
         }
@@ -1063,7 +1088,7 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
 }
 
 unsigned msm_lat_window() {
-    static const unsigned c = [] { const char* e = getenv("ZKGPU_LAT_C"); int v = e ? atoi(e) : 8; return (unsigned)((v >= 6 && v <= 10) ? v : v == 0 ? 0 : 8); }();
+    static const unsigned c = [] { const char* e = getenv("ZKGPU_LAT_C"); int v = e ? atoi(e) : 9; return (unsigned)((v >= 6 && v <= 10) ? v : v == 0 ? 0 : 9); }();
     return c;
 }
 
@@ -1126,18 +1151,19 @@ void msm_lat_run(const MsmPlan& plan, const fr_t* const* d_scalars, uint32_t bas
 }
 
 // ---- direct path, host side ----
-size_t msm_direct_points_per_basis(size_t n) { return (size_t)ZK_DIRECT_W * n * ZK_DIRECT_D; }
+size_t msm_direct_points_per_basis(size_t n) { const unsigned c = msm_lat_window(); return (size_t)direct_W(c) * n * direct_D(c); }
 bool msm_direct_enabled() {
     static const bool on = [] { const char* e = getenv("ZKGPU_DIRECT"); return e ? atoi(e) != 0 : true; }();
-    return on && msm_lat_window() == ZK_DIRECT_C;
+    return on && (msm_lat_window() == 8 || msm_lat_window() == 9);
 }
 // window_table: T[w][i] = 2^(8 w) * base[i] (the latency plan's table for c = 8, W = 32); direct[(w * n + i) * D + d - 1] = d * T[w][i]
 void msm_direct_build(const g1_affine_t* d_window_table, size_t n, g1_affine_t* d_direct, cudaStream_t st) {
-    DevBuf<g1_xyzz_t> tmp(n * ZK_DIRECT_D);
-    DevBuf<fq_t> pre(n * ZK_DIRECT_D);
-    for (unsigned w = 0; w < ZK_DIRECT_W; ++w) {
-        ZK_LAUNCH(k_direct_multiples, ceil_div(n, 64), 64, 0, st, d_window_table + (size_t)w * n, tmp.p, (unsigned)n);
-        ZK_LAUNCH(k_direct_normalize, ceil_div(n, 64), 64, 0, st, tmp.p, pre.p, d_direct + (size_t)w * n * ZK_DIRECT_D, (unsigned)n);
+    const unsigned c = msm_lat_window(), W = direct_W(c), D = direct_D(c);
+    DevBuf<g1_xyzz_t> tmp(n * D);
+    DevBuf<fq_t> pre(n * D);
+    for (unsigned w = 0; w < W; ++w) {
+        ZK_LAUNCH(k_direct_multiples, ceil_div(n, 64), 64, 0, st, d_window_table + (size_t)w * n, tmp.p, (unsigned)n, D);
+        ZK_LAUNCH(k_direct_normalize, ceil_div(n, 64), 64, 0, st, tmp.p, pre.p, d_direct + (size_t)w * n * D, (unsigned)n, D);
     }
     ZK_CUDA(cudaStreamSynchronize(st));
 }
@@ -1149,7 +1175,8 @@ void msm_direct_run(const fr_t* const* d_scalars, uint32_t basis_mask, size_t ta
     for (size_t m = 0; m < ZK_LAT_MAX_M; ++m) A.sc[m] = d_scalars[m < M ? m : 0];
     A.basis_mask = basis_mask; A.table_stride = table_stride; A.n = (unsigned)n; A.tstride = (unsigned)tstride;
     // CTAs per MSM: all CTAs of the launch resident at once (148 SMs x 4 CTAs of 128 threads at 128 registers), at most one unit each
-    const unsigned units = ceil_div(n, 128) * (ZK_DIRECT_W / ZK_DIRECT_WG);
+    const unsigned c = msm_lat_window();
+    const unsigned units = ceil_div(n, 128) * ((direct_W(c) + ZK_DIRECT_WG - 1) / ZK_DIRECT_WG);
     unsigned ctas = (unsigned)(((size_t)148 * 4) / M);
     if (ctas > units) ctas = units;
     if (ctas > 256) ctas = 256;
@@ -1159,7 +1186,8 @@ void msm_direct_run(const fr_t* const* d_scalars, uint32_t basis_mask, size_t ta
     ws.partial.ensure(M * ctas);
     {
         KtScope kt(KT_MSM_BUCKETS, st);
-        ZK_LAUNCH(k_direct_sum, dim3(ctas, (unsigned)M), 128, 0, st, A, d_direct, units, ws.partial.p);
+        if (c == 8) ZK_LAUNCH(k_direct_sum<8>, dim3(ctas, (unsigned)M), 128, 0, st, A, d_direct, units, ws.partial.p);
+        else ZK_LAUNCH(k_direct_sum<9>, dim3(ctas, (unsigned)M), 128, 0, st, A, d_direct, units, ws.partial.p);
     }
     KtScope kt(KT_MSM_REDUCE, st);
     ZK_LAUNCH(k_direct_fold, (unsigned)M, folded, folded * sizeof(g1_xyzz_t), st, ws.partial.p, ctas, d_out_affine);

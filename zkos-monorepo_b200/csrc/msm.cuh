@@ -43,12 +43,12 @@ void msm_run(const MsmPlan& plan, const fr_t* d_scalars, const g1_affine_t* d_ba
 // n scalars at d_scalars[m] (host array of device pointers) and points from d_tables + (bit m of basis_mask) * table_stride.
 // Affine results (normalised) in d_out_affine[m].
 #define ZK_LAT_MAX_M 32
-unsigned msm_lat_window();   // window width of the latency tables (ZKGPU_LAT_C, default 8; 0 disables the latency path)
+unsigned msm_lat_window();   // window width of the latency tables (ZKGPU_LAT_C, default 9; 0 disables the latency path)
 void msm_lat_run(const MsmPlan& plan, const fr_t* const* d_scalars, uint32_t basis_mask, size_t table_stride, const g1_affine_t* d_tables,
                  size_t M, g1_affine_t* d_out_affine, MsmWorkspace& ws, cudaStream_t st);
 // Direct path (no buckets): a table of EVERY multiple d * 2^(8 w) * G_i, d = 1 .. 128, built from the c = 8 window table at SRS
 // registration (msm_direct_points_per_basis(n) points per basis); an MSM is the plain sum of n * 32 table entries.
-bool msm_direct_enabled();     // ZKGPU_DIRECT (default on) and the latency tables use c = 8
+bool msm_direct_enabled();     // ZKGPU_DIRECT (default on) and the latency tables use c = 8 or 9
 size_t msm_direct_points_per_basis(size_t n);
 void msm_direct_build(const g1_affine_t* d_window_table, size_t n, g1_affine_t* d_direct, cudaStream_t st);
 void msm_direct_run(const fr_t* const* d_scalars, uint32_t basis_mask, size_t table_stride, const g1_affine_t* d_direct, size_t n, size_t tstride,

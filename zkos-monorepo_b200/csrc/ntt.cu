@@ -239,6 +239,72 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) k_ntt_cluste
     cluster.sync();   // the partner may still be reading this CTA's tile
 }
 
+// The same transform by a cluster of EIGHT CTAs of 128 threads (32 KB tile each): CTA r of the cluster transforms the
+// subsequence j = brev3(r) (mod 8) — the elements whose bit-reversed position has r in its top three bits — through 10 local
+// stages, and the last THREE stages run as one radix-8 butterfly per output index k' < 1024 across the eight tiles (one local,
+// seven read through distributed shared memory); CTA r produces k' in [128 r, 128 r + 128) and stores eight coalesced runs.
+// Against the two-CTA version: small CTAs (up to four per SM from different clusters, so one cluster's barriers are covered by
+// another's butterflies) instead of one 512-thread CTA per SM.
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(128, 4) k_ntt_cluster8(const NttPass P) {
+    extern __shared__ uint4 sm4[];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    const unsigned rho = ((rank & 1u) << 2) | (rank & 2u) | (rank >> 2);   // brev3(rank)
+    const unsigned total = 1u << P.log_m;          // log_m = log_N - 3, log_C = 0
+    const size_t poly = blockIdx.x >> 3;
+    const fr_t* in = P.in + (poly / P.in_inner) * P.in_outer_stride + (poly % P.in_inner) * P.in_poly_stride;
+    fr_t* out = P.out + (poly / P.out_inner) * P.out_outer_stride + (poly % P.out_inner) * P.out_poly_stride;
+    for (unsigned el = threadIdx.x; el < total; el += blockDim.x) {
+        const size_t gi = 8 * (size_t)el + rho;   // index within the polynomial
+        const bool valid = gi < P.in_valid;
+        fr_t v = valid ? fe_load(in + gi) : fr_t::zero();
+        if (P.pre_coset && valid) {
+            unsigned r3 = (unsigned)(gi % 3);
+            if (r3 == 1) v = v * P.cs1; else if (r3 == 2) v = v * P.cs2;
+        }
+        if (P.pre_table && valid) v = v * fe_ldg(P.pre_table + (((size_t)(poly % P.pre_count)) << P.log_N) + gi);
+        tile_st(sm4, total, __brev(el) >> (32 - P.log_m), v);
+    }
+    __syncthreads();
+    tile_stages(P, sm4);
+    cluster.sync();   // all eight sub-transforms done (and every input consumed: in-place transforms may now be overwritten)
+    const unsigned per = total >> 3;
+    for (unsigned i = threadIdx.x; i < per; i += blockDim.x) {
+        const unsigned k = rank * per + i;          // local index k' in every tile; outputs (r << log_m) | k
+        fr_t x[8];
+#pragma unroll
+        for (unsigned r = 0; r < 8; ++r) x[r] = tile_ld(r == rank ? sm4 : cluster.map_shared_rank(sm4, r), total, k);
+#pragma unroll
+        for (unsigned st = 0; st < 3; ++st) {
+            const unsigned s = P.log_m + st;        // stage: pairs differ in bit st of r (bit s of the position)
+            const unsigned sh = P.log_N - s - 1;
+#pragma unroll
+            for (unsigned q = 0; q < 4; ++q) {
+                const unsigned lo = ((q >> st) << (st + 1)) | (q & ((1u << st) - 1));
+                const unsigned hi = lo | (1u << st);
+                const unsigned jj = ((lo & ((1u << st) - 1)) << P.log_m) | k;   // position bits below the stage
+                fr_t t = x[hi];
+                if (jj) t = t * fe_ldg(P.tw + ((size_t)jj << sh));
+                x[hi] = x[lo] - t;
+                x[lo] = x[lo] + t;
+            }
+        }
+#pragma unroll
+        for (unsigned r = 0; r < 8; ++r) {
+            const unsigned o = (r << P.log_m) | k;
+            fr_t v = x[r];
+            if (P.post_coset) {
+                const unsigned r3 = o % 3;
+                if (r3 == 1) v = v * P.cs1; else if (r3 == 2) v = v * P.cs2;
+            }
+            if (P.has_scale) v = v * P.scale;
+            fe_store(out + o, v);
+        }
+    }
+    cluster.sync();   // the partners may still be reading this CTA's tile
+}
+
 // tw[i] = w^i for i < count, from pows[b] = w^(2^b)
 __global__ void k_twiddles(fr_t* tw, size_t count, const fr_t* pows, unsigned nbits) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -359,8 +425,18 @@ static bool ntt_use_cluster() {
     return on;
 }
 
+// CTAs per cluster of the 2^13 transform: 8 (default) or 2 (ZKGPU_NTT_CLUSTER=2)
+static size_t ntt_cluster_min_batch() {
+    static const size_t v = [] { const char* e = getenv("ZKGPU_NTT_CLUSTER_MIN"); long x = e ? atol(e) : 0; return x > 0 ? (size_t)x : NTT_CLUSTER_MIN_BATCH; }();
+    return v;
+}
+static unsigned ntt_cluster_size() {
+    static const unsigned r = [] { const char* e = getenv("ZKGPU_NTT_CLUSTER"); return (e && atoi(e) == 2) ? 2u : 8u; }();
+    return r;
+}
+
 size_t ntt_scratch_elems(unsigned log_n, size_t batch) {
-    if (log_n == NTT_CLUSTER_LOG && ntt_use_cluster() && batch >= NTT_CLUSTER_MIN_BATCH) return 0;
+    if (log_n == NTT_CLUSTER_LOG && ntt_use_cluster() && batch >= ntt_cluster_min_batch()) return 0;
     return log_n > NTT_SINGLE_PASS_MAX_LOG ? batch << log_n : 0;
 }
 
@@ -397,18 +473,23 @@ void ntt_run(const NttJob& J, cudaStream_t st) {
         launch_pass(P, J.batch, st);
         return;
     }
-    if (log_N == NTT_CLUSTER_LOG && ntt_use_cluster() && J.batch >= NTT_CLUSTER_MIN_BATCH) {
+    if (log_N == NTT_CLUSTER_LOG && ntt_use_cluster() && J.batch >= ntt_cluster_min_batch()) {
+        const unsigned log_r = ntt_cluster_size() == 2 ? 1 : 3;
         P.in = J.in; P.out = J.out;
-        P.log_m = log_N - 1; P.log_C = 0; P.swz_q = pick_swz(P.log_m, 0);
+        P.log_m = log_N - log_r; P.log_C = 0; P.swz_q = pick_swz(P.log_m, 0);
         P.tiles_per_poly = 1;
         P.pre_coset = J.pre_coset; P.post_coset = J.post_coset;
         P.has_scale = J.has_scale; P.scale = J.scale;
         P.first_window_trivial = (P.in_valid * 8 <= N) ? 1 : 0;
-        ZK_REQUIRE(2 * J.batch < (1ull << 31), "ntt: grid too large");
-        static DeviceOnce once;
-        once.run([] { ZK_CUDA(cudaFuncSetAttribute(k_ntt_cluster2, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024)); });
+        ZK_REQUIRE((J.batch << log_r) < (1ull << 31), "ntt: grid too large");
         KtScope kt(KT_NTT, st);
-        ZK_LAUNCH(k_ntt_cluster2, (unsigned)(2 * J.batch), 512, (size_t)128 * 1024, st, P);
+        if (log_r == 1) {
+            static DeviceOnce once;
+            once.run([] { ZK_CUDA(cudaFuncSetAttribute(k_ntt_cluster2, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024)); });
+            ZK_LAUNCH(k_ntt_cluster2, (unsigned)(2 * J.batch), 512, (size_t)128 * 1024, st, P);
+        } else {
+            ZK_LAUNCH(k_ntt_cluster8, (unsigned)(8 * J.batch), 128, (size_t)32 * 1024, st, P);
+        }
         return;
     }
     ZK_REQUIRE(J.scratch != nullptr, "ntt: scratch buffer required for two-pass transforms");

@@ -1259,7 +1259,8 @@ static void prove_batch_on_device(PkEntry& pk, const BatchArgs& a) {
     // the IMAD pipe find more IMAD-bound work of other streams to overlap with), two from two on.
     unsigned workers = (g_ktime_on || g_trace) ? 1 : nsub >= 6 ? 3 : nsub >= 2 ? 2 : 1;
     if (const char* e = getenv("ZKGPU_PROVER_WORKERS")) { int v = atoi(e); if (v >= 1 && v <= (int)BATCH_WORKERS && (unsigned)v < workers) workers = (unsigned)v; }
-    if (workers >= 2 && Bmax > 1) { Bmax = std::max<size_t>(1, std::min(Bmax, (m + 2 * workers - 1) / (2 * workers))); nsub = (m + Bmax - 1) / Bmax; }
+    static const unsigned per_worker = [] { const char* e = getenv("ZKGPU_SUBBATCHES_PER_WORKER"); int v = e ? atoi(e) : 0; return (unsigned)(v >= 1 && v <= 8 ? v : 2); }();
+    if (workers >= 2 && Bmax > 1) { Bmax = std::max<size_t>(1, std::min(Bmax, (m + per_worker * workers - 1) / (per_worker * workers))); nsub = (m + Bmax - 1) / Bmax; }
     // sub-batches as (offset, count).  With host advice the very first one is a quarter of the usual size: nothing can hide its
     // upload, so the GPU should start on a short one while the other worker's full-size upload is still in flight.
     std::vector<std::pair<size_t, size_t>> segs;
