@@ -977,6 +977,8 @@ static void prove_sub_batch(PkEntry& pk, ProverWs& W, const BatchView& V) {
         ea.t_inv = pk.t_inv.p; ea.ext_tw = pk.ext_tw; ea.delta_pows = pk.delta_pows.p; ea.cols = pk.cols.p; ea.ch = W.ch.p;
         ea.prog = pk.prog.p; ea.gate_off = pk.gate_off.p; ea.constants = pk.constants.p;
         ea.adv_q = pk.adv_q.p; ea.fix_q = pk.fix_q.p; ea.inst_q = pk.inst_q.p;
+        ea.n_prog = (unsigned)(pk.prog.n / 2); ea.n_adv_q = (unsigned)cs.advice_queries.size(); ea.n_fix_q = (unsigned)cs.fixed_queries.size();
+        ea.n_inst_q = (unsigned)cs.instance_queries.size();
         ea.num_gates = (unsigned)cs.gates.size(); ea.A = pk.A; ea.S = pk.S; ea.chunk = pk.chunk; ea.P = pk.P; ea.k = pk.k; ea.ek = pk.ek;
         ea.rotation_last = pk.rot_last; ea.zeta = pk.zeta; ea.Qc = pk.Qc;
         ea.lk_ext = W.lk_ext.p; ea.lk_ext_proof_stride = 3 * L * en; ea.lp = lookup_progs(pk);

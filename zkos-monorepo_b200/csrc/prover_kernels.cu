@@ -4,6 +4,7 @@
 // poly/kzg/multiopen/shplonk/prover.rs; every kernel is checked bit-for-bit through whole-proof
 // byte equality against the CPU oracle (tests/test_gpu_prover.py).
 #include "prover_kernels.cuh"
+#include <cstdlib>
 #include "plonk_types.hpp"
 
 namespace zk {
@@ -262,6 +263,18 @@ void launch_chacha_poly(const uint8_t* seeds, fr_t* out, size_t n, size_t B, siz
 __global__ void __launch_bounds__(128) k_eval_h(const EvalHArgs a, fr_t* h, size_t B) {
     // Rows are coset-major: row i = c * n + r is the point g_c * omega^r, g_c = zeta * ext_omega^c, c < Qc.  `en` below is
     // the number of rows per column (Qc * n), not the size of halo2's extended domain.
+    extern __shared__ uint32_t eh_sm[];
+    uint32_t* s_prog = eh_sm;                                   // [2 * n_prog]
+    uint32_t* s_goff = s_prog + 2 * a.n_prog;                   // [num_gates + 1]
+    int32_t* s_advq = reinterpret_cast<int32_t*>(s_goff + a.num_gates + 1);   // [2 * n_adv_q]
+    int32_t* s_fixq = s_advq + 2 * a.n_adv_q;
+    int32_t* s_instq = s_fixq + 2 * a.n_fix_q;
+    for (unsigned t = threadIdx.x; t < 2 * a.n_prog; t += blockDim.x) s_prog[t] = a.prog[t];
+    for (unsigned t = threadIdx.x; t < a.num_gates + 1; t += blockDim.x) s_goff[t] = a.gate_off[t];
+    for (unsigned t = threadIdx.x; t < 2 * a.n_adv_q; t += blockDim.x) s_advq[t] = a.adv_q[t];
+    for (unsigned t = threadIdx.x; t < 2 * a.n_fix_q; t += blockDim.x) s_fixq[t] = a.fix_q[t];
+    for (unsigned t = threadIdx.x; t < 2 * a.n_inst_q; t += blockDim.x) s_instq[t] = a.inst_q[t];
+    __syncthreads();
     const size_t n = (size_t)1 << a.k;
     const size_t en = (size_t)a.Qc << a.k;
     // blocks of one row range are adjacent across the B proofs, so the proving-key columns they share stay in L2
@@ -275,12 +288,12 @@ __global__ void __launch_bounds__(128) k_eval_h(const EvalHArgs a, fr_t* h, size
     const fr_t y = fe_ldg(&a.ch[b].y);
     auto rot = [&](int r) -> size_t { return cbase | ((i + (size_t)(long)r) & (n - 1)); };
 
-    auto fixed_at = [&](uint32_t q) { return fe_ldg(a.fixed_ext + (size_t)a.fix_q[2 * q] * en + rot(a.fix_q[2 * q + 1])); };
-    auto advice_at = [&](uint32_t q) { return fe_load(adv + (size_t)a.adv_q[2 * q] * en + rot(a.adv_q[2 * q + 1])); };
-    auto inst_at = [&](uint32_t q) { return fe_load(adv + (size_t)a.A * en + rot(a.inst_q[2 * q + 1])); };
+    auto fixed_at = [&](uint32_t q) { return fe_ldg(a.fixed_ext + (size_t)s_fixq[2 * q] * en + rot(s_fixq[2 * q + 1])); };
+    auto advice_at = [&](uint32_t q) { return fe_load(adv + (size_t)s_advq[2 * q] * en + rot(s_advq[2 * q + 1])); };
+    auto inst_at = [&](uint32_t q) { return fe_load(adv + (size_t)a.A * en + rot(s_instq[2 * q + 1])); };
     fr_t v = fr_t::zero();
     for (unsigned g = 0; g < a.num_gates; ++g)
-        v = v * y + run_expr(a.prog, a.gate_off[g], a.gate_off[g + 1], a.constants, fixed_at, advice_at, inst_at);
+        v = v * y + run_expr(s_prog, s_goff[g], s_goff[g + 1], a.constants, fixed_at, advice_at, inst_at);
     if (a.P) {
         const fr_t* z = a.z_ext + b * a.z_ext_proof_stride;
         const fr_t beta = fe_ldg(&a.ch[b].beta), gamma = fe_ldg(&a.ch[b].gamma);
@@ -341,7 +354,12 @@ __global__ void __launch_bounds__(128) k_eval_h(const EvalHArgs a, fr_t* h, size
 void launch_eval_h(const EvalHArgs& a, fr_t* h, size_t B, cudaStream_t st) {
     size_t rows = (size_t)a.Qc << a.k;
     KtScope kt(KT_EVAL_H, st);
-    if (B) ZK_LAUNCH(k_eval_h, (unsigned)(ceil_div(rows, 128) * B), 128, 0, st, a, h, B);
+    // (Measured dead end, round 2: four threads per row — one warp per share of the terms, combined through shared memory — for the
+    // single-proof regime: bit-identical, and no faster (250 us either way at 41 k rows): the row's time is not its ~190 dependent
+    // products but the interpreter's dependent operand loads, which a split does not shorten.)
+    const size_t smem = ((size_t)2 * a.n_prog + a.num_gates + 1 + 2 * ((size_t)a.n_adv_q + a.n_fix_q + a.n_inst_q)) * sizeof(uint32_t);
+    ZK_REQUIRE(smem <= 40 * 1024, "eval_h: gate programs too large for shared memory");
+    if (B) ZK_LAUNCH(k_eval_h, (unsigned)(ceil_div(rows, 128) * B), 128, smem, st, a, h, B);
 }
 
 template <int MAXQ>

@@ -91,6 +91,9 @@ struct EvalHArgs {
     const fr_t* lk_ext; size_t lk_ext_proof_stride;
     LookupProgs lp;
     unsigned num_gates, A, S, chunk, P, k, ek;
+    // table sizes (entries): the gate programs and the query tables are staged in shared memory by every CTA, so that an operand
+    // costs one global load (the column value) instead of a chain of three (instruction -> query -> value)
+    unsigned n_prog, n_adv_q, n_fix_q, n_inst_q;
     unsigned Qc;  // cosets of the size-n subgroup the quotient is evaluated on (= number of quotient pieces)
     int rotation_last;
     fr_t zeta;  // coset generator (Montgomery)
