@@ -170,7 +170,7 @@ struct ProverWs {
     HostPinned h_aff, h_evals, h_stage;
 };
 
-static const unsigned BATCH_WORKERS = 3;   // pipeline workers of a zkgpu_prove_batch call
+static const unsigned BATCH_WORKERS = 4;   // pipeline workers of a zkgpu_prove_batch call (at most)
 static const unsigned COALESCE_WORKERS = 3;   // dispatcher threads (per device) behind zkgpu_prove: one uploads while two compute
 struct PkEntry {   // one replica per selected device
     Context* C = nullptr;
@@ -1258,8 +1258,9 @@ static void prove_batch_on_device(PkEntry& pk, const BatchArgs& a) {
     // use a single worker (per-kernel durations are only meaningful when launches do not share the GPU).
     size_t nsub = (m + Bmax - 1) / Bmax;
     // Three workers from six sub-batches on (measured 646 -> 655 proofs/s: the digit sort and the other kernels that do not live on
-    // the IMAD pipe find more IMAD-bound work of other streams to overlap with), two from two on.
-    unsigned workers = (g_ktime_on || g_trace) ? 1 : nsub >= 6 ? 3 : nsub >= 2 ? 2 : 1;
+    // the IMAD pipe find more IMAD-bound work of other streams to overlap with), two from two on; a fourth when the advice is already
+    // resident (round 2: 699.8 -> 705.9 proofs/s; with host advice its extra background upload costs more than it gives, 680 -> 675).
+    unsigned workers = (g_ktime_on || g_trace) ? 1 : (nsub >= 8 && a.advice_on_device) ? 4 : nsub >= 6 ? 3 : nsub >= 2 ? 2 : 1;
     if (const char* e = getenv("ZKGPU_PROVER_WORKERS")) { int v = atoi(e); if (v >= 1 && v <= (int)BATCH_WORKERS && (unsigned)v < workers) workers = (unsigned)v; }
     static const unsigned per_worker = [] { const char* e = getenv("ZKGPU_SUBBATCHES_PER_WORKER"); int v = e ? atoi(e) : 0; return (unsigned)(v >= 1 && v <= 8 ? v : 2); }();
     if (workers >= 2 && Bmax > 1) { Bmax = std::max<size_t>(1, std::min(Bmax, (m + per_worker * workers - 1) / (per_worker * workers))); nsub = (m + Bmax - 1) / Bmax; }
