@@ -3,7 +3,7 @@
 set -u
 TAG=${1:-r01}
 i=0
-for spec in 'k_msm_buckets$:2:8' 'k_eval_h:0:1' 'k_msm_reduce$:2:1' 'k_msm_sort_smem:2:1' 'k_ntt_cluster2:1:2' 'k_coset_combine:0:1' 'k_msm_heavy:2:1' 'k_batch_inverse:0:1'; do
+for spec in 'k_msm_buckets$:2:8' 'k_eval_h:0:1' 'k_msm_reduce$:2:1' 'k_msm_sort_smem:2:1' 'k_ntt_cluster8:1:2' 'k_coset_combine:0:1' 'k_msm_heavy:2:1' 'k_batch_inverse:0:1'; do
     IFS=: read -r name skip count <<< "$spec"
     ncu --set full --clock-control none --import-source on -k "regex:$name" -s "$skip" -c "$count" -f -o /tmp/prof_${TAG}_$i \
         python tools/prover_perf.py 128 withdraw 1 > gpurun_out/ncu_k_${TAG}_$i.log 2>&1
