@@ -284,7 +284,11 @@ class Env:
         L.zkgpu_kernel_timing(1)
         for s in range(len(KT_NAMES)):
             L.zkgpu_kernel_times(s, None, None, 1)
+        L.zkgpu_msm_additions(None, 1)
         ms_step = self.timed(fn, 1)
+        adds = C.c_uint64(0)
+        L.zkgpu_msm_additions(C.byref(adds), 1)
+        self.last_msm_additions = adds.value
         out = {}
         for s, nm in enumerate(KT_NAMES):
             ms, cnt = C.c_double(0), C.c_uint64(0)
@@ -364,6 +368,7 @@ def run_proofs(env, shape_name, M, steps, warmup, full):
         res["value"], res["ms_value"] = total * steps / (ms_value / 1e3), ms_value
         res["proofs_value"] = proofs.copy()
         res["ktimes"], res["ms_ktimed"] = env.ktimes(step_dev)
+        res["msm_additions"] = env.last_msm_additions
         if full:   # single-proof latency (the metric's second half): m = 1 through the same call, p50 of 64
             lat = []
             for i in range(68):
@@ -386,6 +391,7 @@ def run_proofs(env, shape_name, M, steps, warmup, full):
         res["clocks"] = sampler.summary()
         res["value"], res["ms_value"], res["proofs_value"] = None, None, proofs.copy()
         res["ktimes"], res["ms_ktimed"] = env.ktimes(step_host)
+        res["msm_additions"] = env.last_msm_additions
     else:
         assert np.array_equal(proofs, res["proofs_value"]), "host-buffer and device-resident paths produced different proofs"
     res["e2e"], res["ms_e2e"] = total * steps / (ms_e2e / 1e3), ms_e2e
@@ -406,7 +412,11 @@ def proofs_rooflines(env, r, steps):
     # NTT = 64 bytes per point per in-place transform, 32 B in + 32 B out per coset of an extension
     c_win = 13 if shape.k >= 12 else 12
     W_win = 254 // c_win + 1
-    fmul_bucket = M * shape.num_msm * n * W_win * 10
+    nominal_adds = M * shape.num_msm * n * W_win
+    # additions actually queued for the bucket kernels in the class-timed step (zero digits are skipped; a column that is constant
+    # over stretches is committed through its differences): the work the achieved rate is computed from
+    adds = r.get("msm_additions") or nominal_adds
+    fmul_bucket = adds * 10
     cn = shape.num_quotients * n
     ntt_bytes_proof = shape.num_ntt * 64 * n + (shape.num_ext_ntt - 1) * (32 * n + 32 * cn) + 64 * cn
     total_k_ms = sum(v[0] for k_, v in kt.items() if k_ != "host_fiat_shamir_gap") or 1.0
@@ -416,8 +426,9 @@ def proofs_rooflines(env, r, steps):
                  "peak": fmul_peak, "unit": "Gfieldmul/s", "traffic": tr_of("k_msm_buckets"),
                  "traffic_note": "DRAM bytes of one 1024-MSM launch (ncu --set full, profiles/%s); algorithmic bytes of that launch: 1.24e9" % traffic_file,
                  "peak_source": "IMAD.WIDE issue rate measured with tools/imad_peak.cu on this pool / 136 multiply-adds per 254-bit Montgomery product",
-                 "algorithmic_note": "n*W mixed additions x 10 products (8M + 2S); the two products of Y3 share one reduction (fe_mul_add2), so the kernel "
-                                     "issues fewer multiply-adds than this count assumes",
+                 "algorithmic_note": "mixed additions counted by the digit sort (zkgpu_msm_additions) x 10 products (8M + 2S); the two products of Y3 "
+                                     "share one reduction (fe_mul_add2), so the kernel issues fewer multiply-adds than this count assumes",
+                 "additions": adds, "additions_if_every_digit_were_nonzero": nominal_adds,
                  "launches": b_ms[1], "ms_total": b_ms[0], "share_of_kernel_time": b_ms[0] / total_k_ms}
     roof_imad["frac"] = roof_imad["achieved"] / roof_imad["peak"] if roof_imad["achieved"] else None
     roof_hbm = {"kernel": "k_ntt_cluster8 (k_ntt_tile below 592 transforms per call)", "bound": "hbm", "achieved": M * ntt_bytes_proof / (n_ms[0] / 1e3) / 1e9 if n_ms[0] else None,
@@ -427,7 +438,7 @@ def proofs_rooflines(env, r, steps):
     roofline = dict(roof_hbm if dom == "ntt_tile" else roof_imad)
     roofline["dominant_class"] = dom
     nb = 1 << (c_win - 1)
-    mul_msm = shape.num_msm * (n * W_win * 10 + 2 * nb * 14)
+    mul_msm = adds * 10 // M + shape.num_msm * 2 * nb * 14     # counted additions of this witness set + the bucket reductions
     mul_ntt = shape.num_ntt * (n // 2) * shape.k + (shape.num_ext_ntt - 1) * shape.num_quotients * ((n // 2) * shape.k + n) + shape.num_quotients * (n // 2) * shape.k
     imad_bound = fmul_peak * 1e9 / (mul_msm + mul_ntt)
     hbm_bound = hbm_peak * 1e9 / ntt_bytes_proof
@@ -435,7 +446,8 @@ def proofs_rooflines(env, r, steps):
     bound = {"msm_fieldmul_per_proof": mul_msm, "ntt_fieldmul_per_proof": mul_ntt, "ntt_bytes_per_proof": ntt_bytes_proof,
              "imad_bound_proofs_per_s": imad_bound, "hbm_bound_proofs_per_s": hbm_bound, "bound_proofs_per_s": min(imad_bound, hbm_bound),
              "achieved_frac_per_gpu": per_gpu / min(imad_bound, hbm_bound),
-             "note": "MSM (bucket additions + bucket reduction) and NTT products only; quotient evaluation, grand products and openings are extra work the bound ignores"}
+             "note": "MSM (the bucket additions this witness set needs + bucket reduction) and NTT products only; quotient evaluation, grand products "
+                     "and openings are extra work the bound ignores"}
     return roofline, roof_hbm, roof_imad, bound
 
 

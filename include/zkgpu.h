@@ -250,6 +250,10 @@ void zkgpu_set_trace(void (*fn)(const char* name, const void* data, size_t bytes
  * Fiat-Shamir round trips (the host hashes the transcript; hidden by the other pipeline workers outside this timing mode). */
 void zkgpu_kernel_timing(int enable);
 int zkgpu_kernel_times(int slot, double* total_ms, uint64_t* launches, int reset);
+/* mixed point additions queued for bucket accumulation by the batched fixed-base MSM path since the last reset, summed over the
+ * devices (zero digits are skipped and a column may be committed through its differences, so the count depends on the data;
+ * bench.py's roofline uses it as the algorithmic work of the dominant kernel).  Synchronises the devices. */
+int zkgpu_msm_additions(uint64_t* total, int reset);
 /* the library's CUDA stream (cudaStream_t) on the primary device after zkgpu_init, for event timing by the caller */
 void* zkgpu_stream(void);
 /* number of kernel launches issued by this library in this process so far */

@@ -73,3 +73,18 @@ void hl_proof_rng(int mode, uint8_t* data, uint64_t* out, size_t n) {
     r.store_state(data);
 }
 }
+#include "msm_digits.cuh"
+extern "C" {
+// csrc/msm_digits.cuh: the integer the digit sort decomposes for point i and its signed c-bit digits.
+// s, next: n Montgomery scalars each; out_mag [n * W] signed digits (int32: +-magnitude), out_flip [n]
+void hl_msm_digits(const uint32_t* s, const uint32_t* next, size_t n, int diff, unsigned c, unsigned W, int32_t* out_digits, uint8_t* out_flip) {
+    for (size_t i = 0; i < n; ++i) {
+        fr_t a, b; memcpy(a.l, s + 8 * i, 32); memcpy(b.l, next + 8 * i, 32);
+        bool flip = false;
+        fr_t d = digit_scalar(a, b, diff != 0, flip);
+        out_flip[i] = flip;
+        for (unsigned w = 0; w < W; ++w) out_digits[i * W + w] = 0;
+        for_each_digit(d.l, c, W, [&](unsigned w, uint32_t mag, bool negative) { out_digits[i * W + w] = (negative != flip) ? -(int32_t)mag : (int32_t)mag; });
+    }
+}
+}

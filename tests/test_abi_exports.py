@@ -94,7 +94,7 @@ def test_rust_bindings_cover_the_header():
     the boundary a patched halo2 would call."""
     rs = open(os.path.join(ROOT, "rust", "zkgpu-sys", "src", "lib.rs")).read()
     declared = set(re.findall(r"pub fn (zkgpu_\w+)", rs))
-    test_only = {"zkgpu_set_trace", "zkgpu_prover_step_seconds", "zkgpu_kernel_timing", "zkgpu_kernel_times", "zkgpu_stream", "zkgpu_launch_count",
+    test_only = {"zkgpu_set_trace", "zkgpu_prover_step_seconds", "zkgpu_kernel_timing", "zkgpu_kernel_times", "zkgpu_msm_additions", "zkgpu_stream", "zkgpu_launch_count",
                  "zkgpu_fr_vec_op", "zkgpu_fr_to_mont", "zkgpu_fr_from_mont", "zkgpu_fr_random", "zkgpu_ntt_fr_batch_dev", "zkgpu_msm_g1_srs_batch_dev"}
     missing = set(declared_symbols()) - declared - test_only
     assert not missing, missing

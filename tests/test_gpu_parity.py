@@ -178,6 +178,47 @@ def test_srs_batch_commit(raw11, params11):
     assert np.array_equal(got[0], O.msm(s[0, :1000], raw11["g"][:1000], threads=8))
 
 
+def test_srs_batch_commit_structured_columns(raw11, params11):
+    """More than 32 commitments per call take the throughput path, whose digit sort may commit a column through its differences
+    against the prefix sums of the bases (csrc/msm.cuh MsmPlan::diff_offset): constant stretches, sorted columns, small negative
+    values, columns for which the plain half stays cheaper, prefixes of the SRS — all equal to the oracle's best_multiexp."""
+    n, m = 2048, 40
+    r = P.R_MOD
+    rng = np.random.default_rng(77)
+    mont = lambda vals: O.to_mont(0, P.int_to_limbs([v % r for v in vals]))
+    big = lambda: int.from_bytes(rng.bytes(40), "little") % r
+    s = O.random_fr(23, n * m).reshape(m, n, 4)
+    v = big()
+    s[0] = mont([v])[0]                                         # constant, full width
+    s[1] = mont([1])[0]                                         # constant one (a grand product without copies)
+    steps = sorted(rng.choice(n, 5, replace=False).tolist()) + [n]
+    col, lo = [], 0
+    for hi in steps:
+        col += [big()] * (hi - lo); lo = hi
+    s[2] = mont(col)                                            # piecewise constant
+    s[3] = mont(sorted(int(x) for x in rng.integers(0, 256, n)))   # a sorted lookup column
+    s[4] = mont([r - 1])[0]                                     # -1 everywhere
+    s[5] = mont([(r - int(x)) % r for x in rng.integers(0, 4, n)])   # small negative values
+    s[6, 1::2] = 0                                              # alternating: twice as many changes as non-zero terms
+    s[7] = 0
+    s[7, 700:1500] = mont([big()])[0]                           # one stretch between zeros
+    s[8] = 0
+    s[9, :-1] = mont([big()])[0]                                # constant up to a different last element
+    s[10] = mont(list(range(n)))                                # every difference is -1
+    s[11] = mont([big()] * 5 + [0] * (n - 5))
+    for basis, key in ((0, "g"), (1, "g_lagrange")):
+        got = params11.commit_batch(basis, s, n)
+        for i in range(14):
+            assert np.array_equal(got[i], O.msm(s[i], raw11[key], threads=8)), (basis, i)
+        for i in (20, 39):
+            assert np.array_equal(got[i], O.msm(s[i], raw11[key], threads=8)), (basis, i)
+    # prefixes of the SRS: the column ends before the bases do (the last difference is the last scalar itself)
+    for cut in (1000, 1, 33):
+        got = params11.commit_batch(1, s[:, :cut].copy(), cut)
+        for i in (0, 1, 2, 3, 4, 9, 10, 12):
+            assert np.array_equal(got[i], O.msm(s[i, :cut], raw11["g_lagrange"][:cut], threads=8)), (cut, i)
+
+
 def test_g_to_lagrange_known_answer(raw11):
     """K6: reproduces the fixture's g_lagrange block (written by halo2's g_to_lagrange)."""
     zkgpu.init(0)

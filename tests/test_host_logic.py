@@ -282,3 +282,35 @@ def test_degree_without_permutation_columns(hl):
     err = C.create_string_buffer(256)
     assert hl.hl_cs_info(blob, C.c_size_t(len(blob)), info.ctypes.data_as(C.c_void_p), err, C.c_size_t(256)) == 0, err.value
     assert int(info[2]) == 3 and int(info[6]) == 2 and int(info[4]) == 1          # degree 3, two quotient pieces, chunk_len 1
+
+
+@pytest.mark.parametrize("c", [9, 12, 13, 14])
+def test_msm_digit_scalar_recodes_to_the_same_value(hl, c):
+    """csrc/msm_digits.cuh: the signed digits the sort emits, with the sign flip of values within 2^224 below r, sum back to s_i
+    (plain) or s_i - s_{i+1} (difference mode) mod r; small negative values and downward steps get a single non-zero digit."""
+    r = P.R_MOD
+    rng = np.random.default_rng(c)
+    W = 254 // c + 1
+    edge = [0, 1, 2, r - 1, r - 2, (r - 1) // 2, (r + 1) // 2, (r + 3) // 2, 1 << (c - 1), (1 << (c - 1)) + 1, (1 << c) - 1, 1 << c, r - (1 << (c - 1)),
+            (1 << 253) - 1, 1 << 253, 255, r - 255, int("1" * 253, 2)]
+    s = edge * len(edge) + [int.from_bytes(rng.bytes(40), "little") % r for _ in range(4000)]
+    nxt = [e for e in edge for _ in edge] + [int.from_bytes(rng.bytes(40), "little") % r for _ in range(3000)] + s[len(edge) ** 2 + 3000:]
+    assert len(s) == len(nxt)
+    sm = P.int_to_limbs([v * P.MONT_R % r for v in s]).view(np.uint32)
+    nm = P.int_to_limbs([v * P.MONT_R % r for v in nxt]).view(np.uint32)
+    for diff in (0, 1):
+        digits = np.zeros((len(s), W), dtype=np.int32)
+        flip = np.zeros(len(s), dtype=np.uint8)
+        hl.hl_msm_digits(sm.ctypes.data_as(C.c_void_p), nm.ctypes.data_as(C.c_void_p), C.c_size_t(len(s)), diff, c, W,
+                         digits.ctypes.data_as(C.c_void_p), flip.ctypes.data_as(C.c_void_p))
+        assert np.abs(digits).max() <= 1 << (c - 1)
+        for i in range(len(s)):
+            want = (s[i] - nxt[i]) % r if diff else s[i]
+            got = sum(int(d) << (c * w) for w, d in enumerate(digits[i]))
+            assert got % r == want, (diff, i)
+            assert bool(flip[i]) == (want != 0 and r - want < 1 << 224)     # values just below r are taken as small negatives
+            assert (got < 0) == bool(flip[i]) and -(1 << 224) < got < r
+            if want in (1, r - 1, 255, r - 255):
+                assert np.count_nonzero(digits[i]) == 1
+            if want == 0:
+                assert not digits[i].any()

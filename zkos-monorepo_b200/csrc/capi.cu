@@ -197,6 +197,14 @@ const char* zkgpu_last_error(void) { return g_last_error.c_str(); }
 uint64_t zkgpu_launch_count(void) { return g_launches.load(); }
 
 void zkgpu_kernel_timing(int enable) { g_ktime_on = enable != 0; }
+int zkgpu_msm_additions(uint64_t* total, int reset) {
+    API_TRY
+    Runtime& R = rt(); R.require();
+    uint64_t sum = 0;
+    for (auto& dp : R.devs) { DeviceScope scope(*dp); ZK_CUDA(cudaDeviceSynchronize()); sum += msm_entries_counter(reset != 0); }
+    if (total) *total = sum;
+    API_END
+}
 int zkgpu_kernel_times(int slot, double* total_ms, uint64_t* launches, int reset) {
     if (slot < 0 || slot >= KT_SLOTS) return ZKGPU_ERR_ARG;
     std::lock_guard<std::mutex> lk(g_kt_mu);
@@ -263,11 +271,21 @@ int zkgpu_srs_register(const uint64_t* g, const uint64_t* g_lagrange, uint32_t k
         cudaStream_t st = C.stream;
         C.pt_buf.ensure(S->n);
         const uint64_t* src[2] = {g, g_lagrange};
+        // second half of each window table: the same windows over the prefix sums of the basis (MsmPlan::diff_offset)
+        const bool with_diff = msm_diff_enabled() && k <= 16 && 2 * S->n * S->plan.W < (1ull << 31);
+        const size_t half = S->n * S->plan.W;
+        DevBuf<g1_affine_t> prefix;
+        if (with_diff) prefix.alloc(S->n);
         for (int b = 0; b < 2; ++b) {
-            S->table[b].alloc(S->n * S->plan.W);
+            S->table[b].alloc(with_diff ? 2 * half : half);
             ZK_CUDA(cudaMemcpyAsync(C.pt_buf.p, src[b], S->n * 64, cudaMemcpyHostToDevice, st));
             msm_precompute_table(S->plan, C.pt_buf.p, S->table[b].p, st);
+            if (with_diff) {
+                msm_prefix_bases(C.pt_buf.p, S->n, prefix.p, st);
+                msm_precompute_table(S->plan, prefix.p, S->table[b].p + half, st);
+            }
         }
+        if (with_diff) { ZK_CUDA(cudaStreamSynchronize(st)); S->plan.diff_offset = half; }
         // narrow-window tables of both bases, back to back, for the latency path (a few MSMs per launch group: single proofs)
         if (msm_lat_window()) {
             S->lat_plan = msm_plan(S->n, true, msm_lat_window());

@@ -16,32 +16,17 @@
 // The group sum is independent of accumulation order and every exceptional case of the addition
 // formulas is handled, so the affine-normalised result is bit-exact against the CPU oracle.
 #include "msm.cuh"
+#include "msm_digits.cuh"
 #include <mutex>
 #include <cstdlib>
 
 namespace zk {
 
-__host__ __device__ __forceinline__ uint32_t get_bits(const uint32_t* l, unsigned pos, unsigned c) {
-    unsigned word = pos >> 5, shift = pos & 31;
-    if (word >= 8) return 0;
-    uint32_t v = l[word] >> shift;
-    if (shift + c > 32 && word + 1 < 8) v |= l[word + 1] << (32 - shift);
-    return v & ((1u << c) - 1);
-}
+struct MsmDims { unsigned c, W, G, nb; unsigned precomp; unsigned n; unsigned tstride; unsigned heavy; unsigned diff_off; size_t inner, outer_stride; };  // heavy: runs longer than this go to k_msm_heavy  // tstride: table stride (points per window)  // diff_off: MsmPlan::diff_offset
 
-// Calls f(w, magnitude in [1, 2^(c-1)], negative) for each non-zero signed digit of canonical scalar s.
-template <class F>
-__host__ __device__ __forceinline__ void for_each_digit(const uint32_t* s, unsigned c, unsigned W, F f) {
-    uint32_t carry = 0;
-    const uint32_t half = 1u << (c - 1);
-    for (unsigned w = 0; w < W; ++w) {
-        uint32_t d = get_bits(s, w * c, c) + carry;
-        if (d > half) { carry = 1; uint32_t mag = (1u << c) - d; if (mag) f(w, mag, true); }
-        else { carry = 0; if (d) f(w, d, false); }
-    }
-}
-
-struct MsmDims { unsigned c, W, G, nb; unsigned precomp; unsigned n; unsigned tstride; unsigned heavy; size_t inner, outer_stride; };  // heavy: runs longer than this go to k_msm_heavy  // tstride: table stride (points per window)
+// mixed additions queued for the bucket kernels by the throughput path's digit sort (one atomic per MSM): what the roofline of
+// bucket accumulation is computed from, since zero digits and difference mode make it depend on the data (zkgpu_msm_additions)
+__device__ unsigned long long g_msm_entries = 0;
 
 __global__ void k_msm_count(const fr_t* __restrict__ scalars, size_t total, MsmDims D, uint32_t* __restrict__ counts) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -119,19 +104,40 @@ __global__ void __launch_bounds__(1024, 1) k_msm_sort_smem(const fr_t* __restric
     uint32_t* om = offsets + m * ((size_t)K + 1);
     uint32_t* em = entries + m * ((size_t)D.n * D.W);
     uint32_t* ord = order + m * (size_t)K;
+    __shared__ uint32_t nz_cnt[2];
     for (unsigned i = threadIdx.x; i < K; i += T) cnt[i] = 0;
     for (unsigned i = threadIdx.x; i < D.heavy + 2; i += T) hist[i] = 0;
+    if (threadIdx.x < 2) nz_cnt[threadIdx.x] = 0;
     __syncthreads();
+    const unsigned lane = threadIdx.x & 31u;
+    // Which half of the table: the scalars against the plain bases, or their differences against the prefix sums of the bases,
+    // whichever has clearly fewer non-zero terms (Montgomery words are zero / equal exactly when the values are).
+    bool diff = false;
+    if (D.diff_off) {
+        uint32_t ns = 0, nd = 0;
+        for (unsigned i = threadIdx.x; i < D.n; i += T) {
+            const fr_t a = fe_load(sc + i);
+            const fr_t b = i + 1 < D.n ? fe_load(sc + i + 1) : fr_t::zero();
+            ns += a.is_zero() ? 0u : 1u;
+            nd += a == b ? 0u : 1u;
+        }
+        for (unsigned o = 16; o; o >>= 1) { ns += __shfl_down_sync(0xffffffffu, ns, o); nd += __shfl_down_sync(0xffffffffu, nd, o); }
+        if (lane == 0) { atomicAdd(&nz_cnt[0], ns); atomicAdd(&nz_cnt[1], nd); }
+        __syncthreads();
+        diff = nz_cnt[1] + nz_cnt[1] / 8 < nz_cnt[0];
+    }
+    const uint32_t ref_off = diff ? D.diff_off : 0u;
     // Histogram.  The digit loop is warp-uniform (every lane walks all W windows of its scalar, zero digits included), so the
     // lanes can vote: a column whose scalars are all equal — a constant grand product, a selector — sends every lane of a warp
     // to the SAME counter in every window, and 32 same-address shared atomics serialise.  When the voting lanes agree on the
     // key, one lane adds their count (warp-aggregated atomic); otherwise every lane issues its own.
-    const unsigned lane = threadIdx.x & 31u;
     const uint32_t hmax = 1u << (c - 1);
     for (unsigned base = 0; base < D.n; base += T) {
         const unsigned i = base + threadIdx.x;
         const bool valid = i < D.n;
-        fr_t s = valid ? from_mont(fe_load(sc + i)) : fr_t::zero();
+        bool flip = false;
+        fr_t s = fr_t::zero();
+        if (valid) s = digit_scalar(fe_load(sc + i), diff && i + 1 < D.n ? fe_load(sc + i + 1) : fr_t::zero(), diff, flip);
         uint32_t carry = 0;
 #pragma unroll
         for (unsigned w = 0; w < W; ++w) {
@@ -170,18 +176,20 @@ __global__ void __launch_bounds__(1024, 1) k_msm_sort_smem(const fr_t* __restric
         ord[atomicAdd(&hist[c > D.heavy ? D.heavy + 1 : c], 1u)] = i;
         om[i] = run; cnt[i] = run; run += c;
     }
-    if (threadIdx.x == T - 1) om[K] = part[T - 1];
+    if (threadIdx.x == T - 1) { om[K] = part[T - 1]; atomicAdd(&g_msm_entries, (unsigned long long)part[T - 1]); }
     __syncthreads();
     for (unsigned base = 0; base < D.n; base += T) {
         const unsigned i = base + threadIdx.x;
         const bool valid = i < D.n;
-        fr_t s = valid ? from_mont(fe_load(sc + i)) : fr_t::zero();
+        bool flip = false;
+        fr_t s = fr_t::zero();
+        if (valid) s = digit_scalar(fe_load(sc + i), diff && i + 1 < D.n ? fe_load(sc + i + 1) : fr_t::zero(), diff, flip);
         uint32_t carry = 0;
 #pragma unroll
         for (unsigned w = 0; w < W; ++w) {
             uint32_t d = get_bits(s.l, w * c, c) + carry, mag;
             bool negative;
-            if (d > hmax) { carry = 1; mag = (1u << c) - d; negative = true; } else { carry = 0; mag = d; negative = false; }
+            if (d > hmax) { carry = 1; mag = (1u << c) - d; negative = !flip; } else { carry = 0; mag = d; negative = flip; }
             const bool nz = mag != 0;
             const unsigned key = (D.precomp ? 0 : w) * D.nb + (mag - 1);
             const unsigned am = __ballot_sync(0xffffffffu, nz);
@@ -194,7 +202,7 @@ __global__ void __launch_bounds__(1024, 1) k_msm_sort_smem(const fr_t* __restric
                 pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(am & ((1u << lane) - 1u));
             } else if (nz) pos = atomicAdd(&cnt[key], 1u);
             if (nz) {
-                uint32_t ref = D.precomp ? w * D.tstride + i : i;
+                uint32_t ref = (D.precomp ? w * D.tstride + i : i) + ref_off;
                 em[pos] = ref | (negative ? 0x80000000u : 0u);
             }
         }
@@ -957,6 +965,22 @@ __global__ void k_precompute_table(const g1_affine_t* __restrict__ bases, g1_aff
     }
 }
 
+// Prefix sums of the bases (Hillis-Steele over global memory: n log n additions, once per SRS).
+__global__ void k_prefix_lift(const g1_affine_t* __restrict__ in, g1_xyzz_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_affine_t p;
+    p.x = fe_load(&in[i].x); p.y = fe_load(&in[i].y);
+    xyzz_store(out + i, p.is_identity() ? g1_xyzz_t::identity() : g1_xyzz_t::from_affine(p));
+}
+__global__ void k_prefix_step(const g1_xyzz_t* __restrict__ in, g1_xyzz_t* __restrict__ out, size_t n, size_t d) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_xyzz_t a = xyzz_load(in + i);
+    if (i >= d) a = xyzz_add(xyzz_load(in + i - d), a);
+    xyzz_store(out + i, a);
+}
+
 __global__ void k_normalize(const g1_xyzz_t* __restrict__ in, g1_affine_t* __restrict__ out, size_t m) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
@@ -1001,6 +1025,7 @@ void MsmWorkspace::ensure(const MsmPlan& p, size_t M) {
 static MsmDims dims_of(const MsmPlan& p) {
     MsmDims D; D.c = p.c; D.W = p.W; D.G = p.G; D.nb = p.nb; D.precomp = p.precomp ? 1 : 0; D.n = (unsigned)p.n; D.tstride = (unsigned)(p.tstride ? p.tstride : p.n);
     D.inner = p.inner ? p.inner : ~(size_t)0; D.outer_stride = p.outer_stride;
+    D.diff_off = (unsigned)p.diff_offset;
     // a run is "heavy" when it is several times the mean run length (and at least ZK_HEAVY_MIN)
     size_t mean = p.entries_per_msm() / (p.K() ? p.K() : 1);
     size_t heavy = 4 * mean < ZK_HEAVY_MIN ? ZK_HEAVY_MIN : 4 * mean;
@@ -1191,6 +1216,33 @@ void msm_direct_run(const fr_t* const* d_scalars, uint32_t basis_mask, size_t ta
     }
     KtScope kt(KT_MSM_REDUCE, st);
     ZK_LAUNCH(k_direct_fold, (unsigned)M, folded, folded * sizeof(g1_xyzz_t), st, ws.partial.p, ctas, d_out_affine);
+}
+
+unsigned long long msm_entries_counter(bool reset) {
+    unsigned long long v = 0;
+    ZK_CUDA(cudaMemcpyFromSymbol(&v, g_msm_entries, sizeof v));
+    if (reset) { const unsigned long long z = 0; ZK_CUDA(cudaMemcpyToSymbol(g_msm_entries, &z, sizeof z)); }
+    return v;
+}
+
+bool msm_diff_enabled() {
+    static const bool on = [] { const char* e = getenv("ZKGPU_MSM_DIFF"); return e ? atoi(e) != 0 : true; }();
+    return on;
+}
+
+void msm_prefix_bases(const g1_affine_t* d_bases, size_t n, g1_affine_t* d_out, cudaStream_t st) {
+    if (n == 0) return;
+    DevBuf<g1_xyzz_t> a, b;
+    a.alloc(n); b.alloc(n);
+    const unsigned grid = (unsigned)ceil_div(n, 128);
+    ZK_LAUNCH(k_prefix_lift, grid, 128, 0, st, d_bases, a.p, n);
+    g1_xyzz_t *cur = a.p, *nxt = b.p;
+    for (size_t d = 1; d < n; d <<= 1) {
+        ZK_LAUNCH(k_prefix_step, grid, 128, 0, st, cur, nxt, n, d);
+        g1_xyzz_t* t = cur; cur = nxt; nxt = t;
+    }
+    ZK_LAUNCH(k_normalize, grid, 128, 0, st, cur, d_out, n);
+    ZK_CUDA(cudaStreamSynchronize(st));   // the scratch buffers go away with this frame
 }
 
 void msm_precompute_table(const MsmPlan& plan, const g1_affine_t* d_bases, g1_affine_t* d_table, cudaStream_t st) {

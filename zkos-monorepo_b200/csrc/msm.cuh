@@ -14,6 +14,10 @@ struct MsmPlan {
     bool precomp = false;
     size_t n = 0;        // scalars per MSM
     size_t tstride = 0;  // precomp: points per window in the table (0 = n)
+    // precomp: the table continues, diff_offset points further on, with the same windows over the PREFIX SUMS P_i = G_0 + ... + G_i
+    // of the bases (0 = no such half).  sum s_i G_i = sum (s_i - s_{i+1}) P_i, so a column that is constant over long stretches
+    // (a grand product outside the rows that carry copies, a sorted lookup column, padding) costs its number of CHANGES.
+    size_t diff_offset = 0;
     // optional two-level scalar addressing: MSM m reads scalars at (m / inner) * outer_stride + (m % inner) * n
     size_t inner = 0, outer_stride = 0;
     size_t K() const { return (size_t)G * nb; }            // buckets per MSM
@@ -55,6 +59,10 @@ void msm_direct_run(const fr_t* const* d_scalars, uint32_t basis_mask, size_t ta
                     size_t M, g1_affine_t* d_out_affine, MsmWorkspace& ws, cudaStream_t st);
 // table[w*n + i] = 2^(c*w) * bases[i], affine
 void msm_precompute_table(const MsmPlan& plan, const g1_affine_t* d_bases, g1_affine_t* d_table, cudaStream_t st);
+// d_out[i] = d_bases[0] + ... + d_bases[i] (affine), i < n; one-off work at SRS registration
+void msm_prefix_bases(const g1_affine_t* d_bases, size_t n, g1_affine_t* d_out, cudaStream_t st);
+unsigned long long msm_entries_counter(bool reset);   // current device; see g_msm_entries in msm.cu
+bool msm_diff_enabled();   // ZKGPU_MSM_DIFF (default on)
 // affine normalisation of m points (one inversion each)
 void g1_normalize(const g1_xyzz_t* d_in, g1_affine_t* d_out, size_t m, cudaStream_t st);
 
