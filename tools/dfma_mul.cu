@@ -1,4 +1,4 @@
-// Correctness + throughput of the FP64-pipe Montgomery product (csrc/fp_dfma.cuh) against the IMAD product.
+// Correctness + throughput of the FP64-pipe Montgomery product (tools/dead_ends/fp_dfma.cuh) against the IMAD product.
 //   correctness: N random pairs + edge values per field, bit-for-bit equality with fr_mul / fq_mul
 //   throughput : dependent product chains — all warps IMAD, all warps DFMA, and a mix (DFMA on `mix` of 8 warps)
 #include <cstdio>
@@ -6,7 +6,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "fp.cuh"
-#include "fp_dfma.cuh"
+#include "dead_ends/fp_dfma.cuh"
 using namespace zk;
 
 template <class F>
