@@ -78,8 +78,10 @@ int zkgpu_msm_g1_bases(uint64_t bases, const uint64_t* scalars, size_t n, uint64
 
 /* ---- SRS-resident MSM: ParamsKZG::{commit, commit_lagrange} (poly/kzg/commitment.rs) -----------
  * zkgpu_srs_register uploads g and g_lagrange (n = 2^k points each, as ParamsKZG holds them;
- * crates/powers-of-tau/lib.rs:71 builds it, :280 `get_g`) once and precomputes the fixed-base window
- * tables.  basis: 0 = g (monomial, `commit`), 1 = g_lagrange (`commit_lagrange`). */
+ * crates/powers-of-tau/lib.rs:71 builds it, :280 `get_g`) once and precomputes, on every selected device, the fixed-base window
+ * tables of both bases (plain and over the prefix sums of the basis, 2 x 10 MiB per basis at k = 13) and, when they fit a quarter of
+ * the free device memory, the tables of all window multiples that serve single commitments (7.8 GB at k = 13; ZKGPU_DIRECT=0 or
+ * ZKGPU_LAT_C=0 to do without).  basis: 0 = g (monomial, `commit`), 1 = g_lagrange (`commit_lagrange`). */
 int zkgpu_srs_register(const uint64_t* g, const uint64_t* g_lagrange, uint32_t k, uint64_t* handle_out);
 int zkgpu_srs_release(uint64_t srs);
 int zkgpu_msm_g1_srs(uint64_t srs, int basis, const uint64_t* scalars, size_t n, uint64_t out_jacobian[12]);

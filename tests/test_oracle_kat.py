@@ -239,3 +239,26 @@ def test_eval_polynomial():
     x = rand_canon(1, P.R_MOD)[0]
     got = P.limbs_to_int(O.from_mont(0, O.eval_polynomial(O.to_mont(0, P.int_to_limbs(a)), O.to_mont(0, P.int_to_limbs([x]))[0])))
     assert got[0] == sum(c * pow(x, i, P.R_MOD) for i, c in enumerate(a)) % P.R_MOD
+
+
+def test_summation_by_parts_identity_of_difference_mode(raw11):
+    """What csrc/msm.cu's difference mode relies on, stated with the oracle's own group operations on the fixture's g_lagrange:
+    sum_i s_i G_i == sum_i (s_i - s_{i+1}) P_i with P_i = G_0 + ... + G_i and s_n = 0 -- for a random column, a piecewise-constant
+    one (whose differences are almost all zero) and a prefix of the bases."""
+    n = 96
+    G = raw11["g_lagrange"][:n]
+    Pfx = np.empty_like(G)
+    acc = np.zeros(8, dtype=np.uint64)
+    for i in range(n):
+        acc = O.g1_op(0, acc, G[i])
+        Pfx[i] = acc
+    r = P.R_MOD
+    rand = rand_canon(n, r)
+    steps = [rand[0]] * 40 + [rand[1]] * 30 + [0] * 6 + [r - 1] * 20
+    for col in (rand, steps, [7] * n, rand[:50]):
+        m = len(col)
+        diffs = [(col[i] - (col[i + 1] if i + 1 < m else 0)) % r for i in range(m)]
+        lhs = O.msm(O.to_mont(0, P.int_to_limbs(col)), G[:m])
+        rhs = O.msm(O.to_mont(0, P.int_to_limbs(diffs)), Pfx[:m])
+        assert np.array_equal(lhs, rhs)
+    assert sum(1 for i in range(n - 1) if steps[i] != steps[i + 1]) == 3
